@@ -1,0 +1,126 @@
+/*
+ * b200gemm.h — C ABI of the B200-native row-major GEMM (libb200gemm.so).
+ *
+ * This header is the drop-in boundary for the hot path of
+ * tpoisonooo/how-to-optimize-gemm: the free function MY_MMult that the
+ * reference's harness links against exactly one object for.  Every entry point
+ * below cites the reference interface it stands behind:
+ *
+ *   b200_gemm_f32     <- cuda/test_MMult.cpp:13-14  (10-arg MY_MMult, device
+ *                        pointers, C = A*B; wrapper cuda/MMult_cuda_12.cu:228-235)
+ *   b200_gemm_f32_host<- aarch64/MMult0.cpp:3-23 / aarch64/test_MMult.cpp:17
+ *                        (9-arg MY_MMult, host pointers, C += A*B)
+ *   b200_gemm_bf16    <- same contraction, bf16 operands (BASELINE config 3; no
+ *                        reference precedent, semantics of cuda/test_MMult.cpp)
+ *   b200_gemm_s8s32   <- aarch64-int8/MMult_4x8_21.c:81-86 (12-arg MY_MMult,
+ *                        int8 x int8 -> int32, C = A*B, any m,n,k)
+ *   b200_gemm_s8s32_host <- aarch64-int8/test_MMult.c:9,98 (host pointers)
+ *
+ * All matrices are ROW-MAJOR: A is m x k (leading dimension lda >= k),
+ * B is k x n (ldb >= n), C is m x n (ldc >= n); leading dimensions are in
+ * ELEMENTS.  The reference only ever passes lda=k, ldb=n, ldc=n
+ * (cuda/test_MMult.cpp:62) and silently ignores them
+ * (cuda/MMult_cuda_12.cu:231-234); this library honours them.
+ *
+ * Device entry points are fully asynchronous on `stream` (a cudaStream_t passed
+ * as void*; NULL = the legacy default stream the reference harness uses,
+ * cuda/test_MMult.cpp:98-110), never synchronise, never allocate per call and
+ * are re-entrant on one stream.  They return 0 on success or a cudaError_t /
+ * negative B200_ERR_* code.  There is NO CPU fallback: without a CUDA device of
+ * compute capability 10.x every compute entry point returns
+ * B200_ERR_NO_DEVICE.
+ */
+#ifndef B200GEMM_H_
+#define B200GEMM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (negative; positive values are cudaError_t) ------------ */
+#define B200_OK                 0
+#define B200_ERR_BAD_ARG       -1   /* null pointer, negative size, ld too small */
+#define B200_ERR_NO_DEVICE     -2   /* no sm_100 device / driver entry point missing */
+#define B200_ERR_UNSUPPORTED   -3   /* mode not available for this dtype */
+#define B200_ERR_TENSORMAP     -4   /* cuTensorMapEncodeTiled rejected the operand */
+
+/* ---- fp32 precision modes (the SURVEY §7 H1 decision, made explicit) ------ */
+enum b200_f32_mode {
+  B200_F32_STRICT = 0,   /* CUDA-core FFMA, fp32 multiply-add, k ascending: the
+                            arithmetic of cuda/MMult_cuda_12.cu:200-206          */
+  B200_F32_TF32   = 1,   /* one tcgen05 kind::tf32 pass (10-bit mantissa inputs,
+                            fp32 accumulate in TMEM)                              */
+  B200_F32_BF16X3 = 2,   /* split-bf16: a=a1+a2+a3, 6 tcgen05 kind::f16 passes,
+                            fp32-class error, tensor cores                        */
+  B200_F32_BF16X2 = 3,   /* split-bf16: a=a1+a2, 3 passes, ~2^-16 relative       */
+  B200_F32_AUTO   = 4    /* library default (see b200_gemm_default_f32_mode)      */
+};
+
+/* ---- bf16 output selector -------------------------------------------------- */
+enum b200_out_type {
+  B200_OUT_F32  = 0,     /* C written as float   (4 B/elem) */
+  B200_OUT_BF16 = 1      /* C written as bf16    (2 B/elem) */
+};
+
+/* Library / device ---------------------------------------------------------- */
+const char* b200_gemm_version(void);
+/* 0 if a usable sm_100 device is current, else B200_ERR_NO_DEVICE. */
+int  b200_gemm_device_ok(void);
+/* Human-readable text for a code returned by this library. */
+const char* b200_gemm_strerror(int code);
+/* Name of the kernel the last call on this thread dispatched to
+ * ("tc_bf16_128x256", "ffma_128x128", ...), for tests and bench evidence. */
+const char* b200_gemm_last_kernel(void);
+/* Number of kernel launches this library has issued since load. */
+unsigned long long b200_gemm_launch_count(void);
+int  b200_gemm_default_f32_mode(void);
+void b200_gemm_set_default_f32_mode(int mode);
+
+/* fp32: C = A*B.  Replaces MY_MMult(cublasHandle_t,m,n,k,dA,lda,dB,ldb,dC,ldc)
+ * (cuda/test_MMult.cpp:13-14,100-103).  DEVICE pointers. */
+int b200_gemm_f32(int m, int n, int k,
+                  const float* dA, int lda, const float* dB, int ldb,
+                  float* dC, int ldc, int precision_mode, void* stream);
+
+/* fp32 with HOST pointers and the CPU harness contract C += A*B
+ * (aarch64/MMult0.cpp:11-19; harness zeroes C first, aarch64/test_MMult.cpp:107).
+ * Stages H2D, runs b200_gemm_f32 on the device, adds into C on the device,
+ * copies back, synchronises.  Plumbing/parity only, never a reported number. */
+int b200_gemm_f32_host(int m, int n, int k,
+                       const float* A, int lda, const float* B, int ldb,
+                       float* C, int ldc, int precision_mode);
+
+/* bf16 operands (raw uint16 bit patterns), fp32 accumulate; C is float or bf16
+ * according to out_type.  DEVICE pointers. */
+int b200_gemm_bf16(int m, int n, int k,
+                   const uint16_t* dA, int lda, const uint16_t* dB, int ldb,
+                   void* dC, int ldc, int out_type, void* stream);
+
+/* int8 x int8 -> int32, exact: C = A*B (aarch64-int8/README.md:8; oracle
+ * aarch64-int8/REF_MMult.c:10-23).  DEVICE pointers. */
+int b200_gemm_s8s32(int m, int n, int k,
+                    const int8_t* dA, int lda, const int8_t* dB, int ldb,
+                    int32_t* dC, int ldc, void* stream);
+
+/* int8 with HOST pointers: what aarch64-int8/test_MMult.c:98 passes. */
+int b200_gemm_s8s32_host(int m, int n, int k,
+                         const int8_t* A, int lda, const int8_t* B, int ldb,
+                         int32_t* C, int ldc);
+
+/* Element-wise helper the bf16 config needs on the device: round-to-nearest-
+ * even fp32 -> bf16 (the rounding SURVEY §8d prescribes for config 3 inputs). */
+int b200_convert_f32_to_bf16(const float* dSrc, uint16_t* dDst, size_t count,
+                             void* stream);
+
+/* Test/diagnostic hook: overrides for the UMMA shared-memory descriptor of the
+ * MN-major B operand (bytes; 0 = library default).  Used only by the probe in
+ * tests/ to pin the descriptor semantics on real hardware. */
+void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GEMM_H_ */

@@ -1,0 +1,261 @@
+/*
+ * oracle.c — CPU restatement of the reference's GEMM hot path.
+ * TEST INFRASTRUCTURE ONLY (see oracle.h).  Parity status: PINNED against
+ * oracle/_ref/libref.so (the reference's own sources) by
+ * tests/test_oracle_vs_ref.py and the vectors under tests/golden/.
+ *
+ * Build: gcc -O3 -ffp-contract=off -mavx2 -mfma -pthread -fPIC -shared
+ * (oracle/Makefile); explicit fmaf() calls become vfmadd, nothing else fuses.
+ * -ffp-contract=off keeps multiply and add separately rounded, which is what
+ * the reference's `g++ -O2` build of aarch64/REF_MMult.cpp produces on x86-64.
+ */
+#define _XOPEN_SOURCE 600
+#include "oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+/* ---- tiny row-parallel helper (this image's gcc has no libgomp) ------------- */
+static int g_threads = 0;
+void oracle_set_threads(int n) { g_threads = n; }
+int oracle_get_threads(void) {
+  if (g_threads > 0) return g_threads;
+  long n = sysconf(_SC_NPROCESSORS_ONLN);
+  return n > 0 ? (int)n : 1;
+}
+typedef void (*row_fn)(int i0, int i1, void* ctx);
+typedef struct { row_fn fn; void* ctx; int i0, i1; } row_job;
+static void* row_tramp(void* p) { row_job* j = (row_job*)p; j->fn(j->i0, j->i1, j->ctx); return NULL; }
+static void par_rows(int m, row_fn fn, void* ctx) {
+  int nt = oracle_get_threads();
+  if (nt > m) nt = m;
+  if (nt <= 1) { fn(0, m, ctx); return; }
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nt);
+  row_job* jobs = (row_job*)malloc(sizeof(row_job) * nt);
+  for (int t = 0; t < nt; t++) {
+    jobs[t].fn = fn; jobs[t].ctx = ctx;
+    jobs[t].i0 = (int)((long long)m * t / nt);
+    jobs[t].i1 = (int)((long long)m * (t + 1) / nt);
+    pthread_create(&th[t], NULL, row_tramp, &jobs[t]);
+  }
+  for (int t = 0; t < nt; t++) pthread_join(th[t], NULL);
+  free(th); free(jobs);
+}
+typedef struct { int n, k; const void* a; int lda; const void* b; int ldb; void* c; int ldc; } mm_ctx;
+
+void oracle_seed(long seed) { srand48(seed); }
+
+/* cuda/random_matrix.cpp:3,6-16 — note the column-index-outer macro
+ * A(i,j) = a[j*lda+i] and the double-precision expression around a float
+ * cast of drand48(). */
+void oracle_random_matrix_cuda(int m, int n, float* a, int lda) {
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < n; j++)
+      a[(size_t)j * lda + i] = (float)(2.0 * (double)(float)drand48() - 1.0);
+}
+
+/* aarch64/random_matrix.cpp:16 */
+void oracle_random_matrix_ones(int m, int n, float* a) {
+  for (size_t i = 0; i < (size_t)m * n; i++) a[i] = 1.0f;
+}
+
+/* aarch64-int8/random_matrix.c:13-21 */
+void oracle_random_int8_ramp(int m, int n, int8_t* a, int lda) {
+  int val = 0;
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < n; j++) {
+      a[(size_t)i * lda + j] = (int8_t)(val % 3);
+      val++;
+    }
+}
+
+void oracle_random_int8_uniform(int m, int n, int8_t* a, int lda, uint64_t seed) {
+  uint64_t s = seed * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < n; j++) {
+      s = s * 6364136223846793005ull + 1442695040888963407ull;
+      uint32_t r = (uint32_t)(s >> 33);
+      a[(size_t)i * lda + j] = (int8_t)((int)(r % 255u) - 127);
+    }
+}
+
+/* aarch64/REF_MMult.cpp:18-28 */
+void oracle_ref_mmult_f32(int m, int n, int k, const float* a, int lda,
+                          const float* b, int ldb, float* c, int ldc) {
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < n; j++)
+      for (int p = 0; p < k; p++)
+        c[(size_t)i * ldc + j] =
+            c[(size_t)i * ldc + j] + a[(size_t)i * lda + p] * b[(size_t)p * ldb + j];
+}
+
+/* aarch64/REF_MMult.cpp:24 as compiled by aarch64/makefile:14 (fused). */
+void oracle_ref_mmult_f32_fma(int m, int n, int k, const float* a, int lda,
+                              const float* b, int ldb, float* c, int ldc) {
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < n; j++)
+      for (int p = 0; p < k; p++)
+        c[(size_t)i * ldc + j] =
+            fmaf(a[(size_t)i * lda + p], b[(size_t)p * ldb + j], c[(size_t)i * ldc + j]);
+}
+
+static void rows_f32_fma(int i0, int i1, void* vc) {
+  mm_ctx* x = (mm_ctx*)vc;
+  const float* a = (const float*)x->a; const float* b = (const float*)x->b; float* c = (float*)x->c;
+  for (int i = i0; i < i1; i++) {
+    float* __restrict ci = c + (size_t)i * x->ldc;
+    for (int p = 0; p < x->k; p++) {
+      const float aip = a[(size_t)i * x->lda + p];
+      const float* __restrict bp = b + (size_t)p * x->ldb;
+      for (int j = 0; j < x->n; j++) ci[j] = fmaf(aip, bp[j], ci[j]);
+    }
+  }
+}
+void oracle_ref_mmult_f32_fma_fast(int m, int n, int k, const float* a, int lda,
+                                   const float* b, int ldb, float* c, int ldc) {
+  mm_ctx x = {n, k, a, lda, b, ldb, c, ldc};
+  par_rows(m, rows_f32_fma, &x);
+}
+
+/* Same per-element operation sequence (c_ij += a_ip*b_pj for p = 0..k-1, each
+ * step rounded to fp32), reordered i,p,j so the inner loop is unit-stride. */
+static void rows_f32(int i0, int i1, void* vc) {
+  mm_ctx* x = (mm_ctx*)vc;
+  const float* a = (const float*)x->a; const float* b = (const float*)x->b; float* c = (float*)x->c;
+  for (int i = i0; i < i1; i++) {
+    float* __restrict ci = c + (size_t)i * x->ldc;
+    for (int p = 0; p < x->k; p++) {
+      const float aip = a[(size_t)i * x->lda + p];
+      const float* __restrict bp = b + (size_t)p * x->ldb;
+      for (int j = 0; j < x->n; j++) ci[j] = ci[j] + aip * bp[j];
+    }
+  }
+}
+void oracle_ref_mmult_f32_fast(int m, int n, int k, const float* a, int lda,
+                               const float* b, int ldb, float* c, int ldc) {
+  mm_ctx x = {n, k, a, lda, b, ldb, c, ldc};
+  par_rows(m, rows_f32, &x);
+}
+
+static void rows_f64acc(int i0, int i1, void* vc) {
+  mm_ctx* x = (mm_ctx*)vc;
+  const float* a = (const float*)x->a; const float* b = (const float*)x->b; double* c = (double*)x->c;
+  for (int i = i0; i < i1; i++) {
+    double* __restrict ci = c + (size_t)i * x->ldc;
+    for (int j = 0; j < x->n; j++) ci[j] = 0.0;
+    for (int p = 0; p < x->k; p++) {
+      const double aip = (double)a[(size_t)i * x->lda + p];
+      const float* __restrict bp = b + (size_t)p * x->ldb;
+      for (int j = 0; j < x->n; j++) ci[j] += aip * (double)bp[j];
+    }
+  }
+}
+void oracle_ref_mmult_f64acc(int m, int n, int k, const float* a, int lda,
+                             const float* b, int ldb, double* c, int ldc) {
+  mm_ctx x = {n, k, a, lda, b, ldb, c, ldc};
+  par_rows(m, rows_f64acc, &x);
+}
+
+/* aarch64-int8/REF_MMult.c:10-23 */
+void oracle_ref_mmult_s8s32(int m, int n, int k, const int8_t* a, int lda,
+                            const int8_t* b, int ldb, int32_t* c, int ldc) {
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < n; j++)
+      for (int p = 0; p < k; p++)
+        c[(size_t)i * ldc + j] =
+            c[(size_t)i * ldc + j] + a[(size_t)i * lda + p] * b[(size_t)p * ldb + j];
+}
+
+/* Integer addition is associative, so any order is bit-identical. */
+static void rows_s8(int i0, int i1, void* vc) {
+  mm_ctx* x = (mm_ctx*)vc;
+  const int8_t* a = (const int8_t*)x->a; const int8_t* b = (const int8_t*)x->b; int32_t* c = (int32_t*)x->c;
+  for (int i = i0; i < i1; i++) {
+    int32_t* __restrict ci = c + (size_t)i * x->ldc;
+    for (int p = 0; p < x->k; p++) {
+      const int32_t aip = a[(size_t)i * x->lda + p];
+      const int8_t* __restrict bp = b + (size_t)p * x->ldb;
+      for (int j = 0; j < x->n; j++) ci[j] += aip * (int32_t)bp[j];
+    }
+  }
+}
+void oracle_ref_mmult_s8s32_fast(int m, int n, int k, const int8_t* a, int lda,
+                                 const int8_t* b, int ldb, int32_t* c, int ldc) {
+  mm_ctx x = {n, k, a, lda, b, ldb, c, ldc};
+  par_rows(m, rows_s8, &x);
+}
+
+/* cuda/compare_matrices.cpp:17-29, NaN-aware. */
+float oracle_compare_matrices_f32(int m, int n, const float* a, int lda,
+                                  const float* b, int ldb) {
+  float max_diff = 0.0f;
+  int saw_nan = 0;
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < n; j++) {
+      float d = a[(size_t)i * lda + j] - b[(size_t)i * ldb + j];
+      if (d != d) saw_nan = 1;
+      d = d < 0.0f ? -d : d;
+      if (d > max_diff) max_diff = d;
+    }
+  return saw_nan ? NAN : max_diff;
+}
+
+/* aarch64-int8/compare_matrices.c:19-31 */
+int32_t oracle_compare_matrices_s32(int m, int n, const int32_t* a, int lda,
+                                    const int32_t* b, int ldb) {
+  int64_t max_diff = 0;
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < n; j++) {
+      int64_t d = (int64_t)a[(size_t)i * lda + j] - (int64_t)b[(size_t)i * ldb + j];
+      if (d < 0) d = -d;
+      if (d > max_diff) max_diff = d;
+    }
+  return max_diff > INT32_MAX ? INT32_MAX : (int32_t)max_diff;
+}
+
+float oracle_max_abs_f32(int m, int n, const float* a, int lda) {
+  float mx = 0.0f;
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < n; j++) {
+      float v = fabsf(a[(size_t)i * lda + j]);
+      if (v != v) return NAN;
+      if (v > mx) mx = v;
+    }
+  return mx;
+}
+
+double oracle_max_err_vs_f64(int m, int n, const float* c, int ldc,
+                             const double* t, int ldt) {
+  double mx = 0.0;
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < n; j++) {
+      double d = fabs((double)c[(size_t)i * ldc + j] - t[(size_t)i * ldt + j]);
+      if (d != d) return NAN;
+      if (d > mx) mx = d;
+    }
+  return mx;
+}
+
+uint16_t oracle_f32_to_bf16(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u && (u & 0x007FFFFFu))
+    return (uint16_t)((u >> 16) | 0x0040u);             /* quiet NaN */
+  uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7FFFu + lsb;                                    /* round to nearest even */
+  return (uint16_t)(u >> 16);
+}
+
+float oracle_bf16_to_f32(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float x;
+  memcpy(&x, &u, 4);
+  return x;
+}
+
+void oracle_round_to_bf16_inplace(size_t count, float* a) {
+  for (size_t i = 0; i < count; i++) a[i] = oracle_bf16_to_f32(oracle_f32_to_bf16(a[i]));
+}
