@@ -1,0 +1,150 @@
+"""how-to-optimize-gemm_b200 — Python host binding of libb200gemm.so (ctypes over the C ABI).
+
+The product is the CUDA library; this module only loads it and forwards pointers.  PyTorch is
+plumbing (device memory, streams, torch.distributed) and is imported lazily, only by the helpers
+that take tensors.  There is NO CPU fallback: if the shared library is missing, import fails
+loudly; if no sm_100 GPU is present, every compute call raises B200GemmError(-2).
+
+Interface mirrored from the reference (file:line in /root/reference):
+  MY_MMult(m, n, k, a, lda, b, ldb, c, ldc)                 aarch64/MMult0.cpp:3   (host, C += A*B)
+  MY_MMult_cuda(handle, m, n, k, dA, lda, dB, ldb, dC, ldc)  cuda/test_MMult.cpp:13 (device, C = A*B)
+  MY_MMult_int8(m, n, k, a, lda, b, ldb, c, ldc)             aarch64-int8/test_MMult.c:9
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200gemm.so")
+
+F32_STRICT, F32_TF32, F32_BF16X3, F32_BF16X2, F32_AUTO = 0, 1, 2, 3, 4
+OUT_F32, OUT_BF16 = 0, 1
+
+EXPORTS = [
+    "b200_gemm_version", "b200_gemm_device_ok", "b200_gemm_strerror", "b200_gemm_last_kernel",
+    "b200_gemm_launch_count", "b200_gemm_default_f32_mode", "b200_gemm_set_default_f32_mode",
+    "b200_gemm_f32", "b200_gemm_f32_host", "b200_gemm_bf16", "b200_gemm_s8s32",
+    "b200_gemm_s8s32_host", "b200_convert_f32_to_bf16", "b200_gemm_debug_set_b_desc",
+]
+
+
+class B200GemmError(RuntimeError):
+    def __init__(self, code, what=""):
+        self.code = code
+        super().__init__(f"b200gemm error {code}: {what}")
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this path.")
+
+lib = C.CDLL(LIB_PATH)
+_vp, _i = C.c_void_p, C.c_int
+lib.b200_gemm_version.restype = C.c_char_p
+lib.b200_gemm_strerror.restype = C.c_char_p
+lib.b200_gemm_strerror.argtypes = [_i]
+lib.b200_gemm_last_kernel.restype = C.c_char_p
+lib.b200_gemm_launch_count.restype = C.c_ulonglong
+lib.b200_gemm_f32.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp]
+lib.b200_gemm_f32_host.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i]
+lib.b200_gemm_bf16.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp]
+lib.b200_gemm_s8s32.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]
+lib.b200_gemm_s8s32_host.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i]
+lib.b200_convert_f32_to_bf16.argtypes = [_vp, _vp, C.c_size_t, _vp]
+lib.b200_gemm_debug_set_b_desc.argtypes = [_i, _i]
+lib.b200_gemm_set_default_f32_mode.argtypes = [_i]
+
+
+def _check(rc):
+    if rc != 0:
+        raise B200GemmError(rc, lib.b200_gemm_strerror(rc).decode())
+
+
+def version():
+    return lib.b200_gemm_version().decode()
+
+
+def last_kernel():
+    return lib.b200_gemm_last_kernel().decode()
+
+
+def launch_count():
+    return int(lib.b200_gemm_launch_count())
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+    return getattr(stream, "cuda_stream", stream)
+
+
+# ---- raw-pointer forms (exact mirrors of the reference signatures) ------------------------------
+def MY_MMult_cuda(handle, m, n, k, dA, lda, dB, ldb, dC, ldc, mode=F32_AUTO, stream=0):
+    """cuda/test_MMult.cpp:13-14 — device pointers (ints), C = A*B.  `handle` is ignored, as the
+    reference's hand kernels ignore it (cuda/MMult_cuda_12.cu:228)."""
+    _check(lib.b200_gemm_f32(m, n, k, dA, lda, dB, ldb, dC, ldc, mode, stream))
+
+
+def MY_MMult(m, n, k, a, lda, b, ldb, c, ldc, mode=F32_AUTO):
+    """aarch64/MMult0.cpp:3-4 — numpy float32 host arrays, C += A*B in place."""
+    _check(lib.b200_gemm_f32_host(m, n, k, a.ctypes.data, lda, b.ctypes.data, ldb, c.ctypes.data, ldc, mode))
+
+
+def MY_MMult_int8(m, n, k, a, lda, b, ldb, c, ldc):
+    """aarch64-int8/test_MMult.c:9,98 — numpy int8 host arrays, int32 C = A*B."""
+    _check(lib.b200_gemm_s8s32_host(m, n, k, a.ctypes.data, lda, b.ctypes.data, ldb, c.ctypes.data, ldc))
+
+
+# ---- tensor forms (torch CUDA tensors; row-major, last dim contiguous) --------------------------
+def _ld(t):
+    assert t.dim() == 2 and t.stride(1) == 1, "row-major 2-D tensor with unit inner stride expected"
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+def gemm_f32(A, B, out=None, mode=F32_AUTO, stream=None):
+    import torch
+    assert A.dtype == torch.float32 and B.dtype == torch.float32 and A.is_cuda and B.is_cuda
+    m, k = A.shape
+    k2, n = B.shape
+    assert k == k2
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=A.device)
+    _check(lib.b200_gemm_f32(m, n, k, A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), out.data_ptr(), _ld(out),
+                             mode, _stream_ptr(stream)))
+    return out
+
+
+def gemm_bf16(A, B, out=None, out_dtype=None, stream=None):
+    import torch
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.is_cuda and B.is_cuda
+    m, k = A.shape
+    k2, n = B.shape
+    assert k == k2
+    if out is None:
+        out = torch.empty((m, n), dtype=out_dtype or torch.float32, device=A.device)
+    ot = OUT_F32 if out.dtype == torch.float32 else OUT_BF16
+    assert out.dtype in (torch.float32, torch.bfloat16)
+    _check(lib.b200_gemm_bf16(m, n, k, A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), out.data_ptr(), _ld(out),
+                              ot, _stream_ptr(stream)))
+    return out
+
+
+def gemm_s8s32(A, B, out=None, stream=None):
+    import torch
+    assert A.dtype == torch.int8 and B.dtype == torch.int8 and A.is_cuda and B.is_cuda
+    m, k = A.shape
+    k2, n = B.shape
+    assert k == k2
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.int32, device=A.device)
+    _check(lib.b200_gemm_s8s32(m, n, k, A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), out.data_ptr(), _ld(out),
+                               _stream_ptr(stream)))
+    return out
+
+
+def convert_f32_to_bf16(src, stream=None):
+    import torch
+    out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    _check(lib.b200_convert_f32_to_bf16(src.data_ptr(), out.data_ptr(), src.numel(), _stream_ptr(stream)))
+    return out

@@ -1,0 +1,404 @@
+// capi.cu — the C ABI of libb200gemm.so (include/b200gemm.h): argument checks, tensor-map
+// construction and caching, kernel selection and launch.  Host-side counterpart of the reference's
+// MY_MMult wrappers (cuda/MMult_cuda_12.cu:228-235; aarch64-int8/MMult_4x8_21.c:81-143).
+//
+// No cuBLAS, no CUTLASS, no CPU fallback: if no sm_100 device is usable every compute entry point
+// fails with B200_ERR_NO_DEVICE.
+#include "../../include/b200gemm.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "gemm_ffma.cuh"
+#include "gemm_generic.cuh"
+#include "gemm_tc.cuh"
+
+using namespace b200;
+
+namespace {
+
+std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_default_f32_mode{-1};
+thread_local const char* t_last_kernel = "none";
+int g_dbg_b_lbo = 0, g_dbg_b_sbo = 0;
+
+struct DeviceInfo {
+  int ok = 0;          // 1 usable, -1 not usable, 0 unknown
+  int sms = 0;
+  int dev = -1;
+};
+std::mutex g_mu;
+DeviceInfo g_dev;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int ensure_device() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); g_dev.ok = -1; return B200_ERR_NO_DEVICE; }
+  if (g_dev.ok == 1 && g_dev.dev == dev) return 0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { cudaGetLastError(); g_dev.ok = -1; return B200_ERR_NO_DEVICE; }
+  if (prop.major != 10) { g_dev.ok = -1; return B200_ERR_NO_DEVICE; }
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !fn) {
+      cudaGetLastError();
+      g_dev.ok = -1;
+      return B200_ERR_NO_DEVICE;
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  g_dev.ok = 1;
+  g_dev.dev = dev;
+  g_dev.sms = prop.multiProcessorCount;
+  return 0;
+}
+
+// ---- tensor-map cache: cuTensorMapEncodeTiled costs microseconds, the harness calls MY_MMult 20x
+// back to back on the same operands (cuda/test_MMult.cpp:100-103).
+struct MapKey {
+  const void* ptr; int dtype; unsigned long long d0, d1, ld_bytes; unsigned b0, b1; int swz; int dev;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && dtype == o.dtype && d0 == o.d0 && d1 == o.d1 && ld_bytes == o.ld_bytes &&
+           b0 == o.b0 && b1 == o.b1 && swz == o.swz && dev == o.dev;
+  }
+};
+struct MapEntry { MapKey key; CUtensorMap map; };
+std::vector<MapEntry> g_maps;
+size_t g_map_next = 0;
+constexpr size_t kMapCache = 64;
+
+// 2-D row-major tensor: dim0 (inner, contiguous) x dim1 rows with pitch ld_bytes.
+int get_map(CUtensorMap* out, const void* ptr, CUtensorMapDataType dt, int elem_bytes,
+            unsigned long long inner, unsigned long long rows, unsigned long long ld_bytes,
+            unsigned box_inner, unsigned box_rows, bool swizzle128) {
+  MapKey key{ptr, (int)dt, inner, rows, ld_bytes, box_inner, box_rows, swizzle128 ? 1 : 0, g_dev.dev};
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& e : g_maps)
+    if (e.key == key) { *out = e.map; return 0; }
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {ld_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = g_encode(&m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  (void)elem_bytes;
+  if (r != CUDA_SUCCESS) return B200_ERR_TENSORMAP;
+  if (g_maps.size() < kMapCache) g_maps.push_back({key, m});
+  else { g_maps[g_map_next] = {key, m}; g_map_next = (g_map_next + 1) % kMapCache; }
+  *out = m;
+  return 0;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int check_args(int m, int n, int k, const void* A, int lda, const void* B, int ldb, const void* C, int ldc) {
+  if (m < 0 || n < 0 || k < 0) return B200_ERR_BAD_ARG;
+  if (m == 0 || n == 0) return 1;            // nothing to do
+  if (!C || ldc < n) return B200_ERR_BAD_ARG;
+  if (k > 0 && (!A || !B || lda < k || ldb < n)) return B200_ERR_BAD_ARG;
+  return 0;
+}
+
+int last_launch_status() {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+  return 0;
+}
+
+template <typename T>
+int launch_zero(int m, int n, T* C, int ldc, cudaStream_t st) {
+  dim3 grid((n + 255) / 256, m < 4096 ? m : 4096);
+  fill_zero_kernel<T><<<grid, 256, 0, st>>>(m, n, C, ldc);
+  g_launches++;
+  t_last_kernel = "fill_zero";
+  return last_launch_status();
+}
+
+template <typename InT, typename OutT>
+int launch_generic(int m, int n, int k, const InT* A, int lda, const InT* B, int ldb, OutT* C, int ldc,
+                   int accumulate, cudaStream_t st, const char* name) {
+  dim3 grid((n + 63) / 64, (m + 63) / 64);
+  gemm_generic_kernel<InT, OutT><<<grid, 256, 0, st>>>(m, n, k, A, lda, B, ldb, C, ldc, accumulate);
+  g_launches++;
+  t_last_kernel = name;
+  return last_launch_status();
+}
+
+// ---- tensor-core launch -------------------------------------------------------------------
+template <int KIND, int BN, int STAGES, typename OutT>
+int launch_tc(int m, int n, int k, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
+              cudaStream_t st, const char* name) {
+  using Cfg = TcConfig<KIND, BN, STAGES>;
+  using T = KindTraits<KIND>;
+  constexpr CUtensorMapDataType dt = KIND == KIND_F16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                   : KIND == KIND_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                       : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  CUtensorMap tmA, tmB;
+  int rc = get_map(&tmA, A, dt, T::ELEM, k, m, (unsigned long long)lda * T::ELEM, Cfg::BK, Cfg::BM, true);
+  if (rc) return rc;
+  rc = get_map(&tmB, B, dt, T::ELEM, n, k, (unsigned long long)ldb * T::ELEM, Cfg::B_BOX_COLS, Cfg::BK, true);
+  if (rc) return rc;
+  TcParams p;
+  p.C = C; p.ldc = ldc; p.M = m; p.N = n; p.K = k;
+  p.tiles_m = (m + Cfg::BM - 1) / Cfg::BM;
+  p.tiles_n = (n + BN - 1) / BN;
+  p.group_m = 16;
+  constexpr int OB = OutBytes<OutT>::V;
+  p.vec_ok = aligned16(C) && ((long long)ldc * OB) % 16 == 0;
+  p.dbg_b_lbo = g_dbg_b_lbo; p.dbg_b_sbo = g_dbg_b_sbo;
+  auto kern = gemm_tc_kernel<KIND, BN, STAGES, OutT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    attr_set = true;
+  }
+  int tiles = p.tiles_m * p.tiles_n;
+  int grid = tiles < g_dev.sms ? tiles : g_dev.sms;
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  g_launches++;
+  t_last_kernel = name;
+  return last_launch_status();
+}
+
+int launch_ffma(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                int accumulate, cudaStream_t st) {
+  using Cfg = FfmaCfg;
+  CUtensorMap tmA, tmB;
+  int rc = get_map(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, k, m, (unsigned long long)lda * 4, Cfg::BK, Cfg::BM, true);
+  if (rc) return rc;
+  rc = get_map(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, n, k, (unsigned long long)ldb * 4, Cfg::BN, Cfg::BK, false);
+  if (rc) return rc;
+  FfmaParams p;
+  p.C = C; p.ldc = ldc; p.M = m; p.N = n; p.K = k;
+  p.vec_ok = aligned16(C) && (ldc % 4) == 0;
+  p.accumulate = accumulate;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_ffma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    attr_set = true;
+  }
+  dim3 grid((n + Cfg::BN - 1) / Cfg::BN, (m + Cfg::BM - 1) / Cfg::BM);
+  gemm_ffma_kernel<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  g_launches++;
+  t_last_kernel = "ffma_128x128x32_tma";
+  return last_launch_status();
+}
+
+bool tma_ok(const void* A, int lda, const void* B, int ldb, int elem) {
+  return aligned16(A) && aligned16(B) && ((long long)lda * elem) % 16 == 0 && ((long long)ldb * elem) % 16 == 0;
+}
+
+int resolve_f32_mode(int mode) {
+  if (mode == B200_F32_AUTO) {
+    int d = g_default_f32_mode.load();
+    if (d < 0) {
+      const char* e = getenv("B200GEMM_F32_MODE");
+      d = e ? atoi(e) : B200_F32_STRICT;
+      if (d < 0 || d >= B200_F32_AUTO) d = B200_F32_STRICT;
+      g_default_f32_mode.store(d);
+    }
+    return d;
+  }
+  return mode;
+}
+
+int gemm_f32_impl(int m, int n, int k, const float* dA, int lda, const float* dB, int ldb, float* dC,
+                  int ldc, int mode, int accumulate, cudaStream_t st) {
+  int rc = check_args(m, n, k, dA, lda, dB, ldb, dC, ldc);
+  if (rc == 1) return 0;
+  if (rc) return rc;
+  rc = ensure_device();
+  if (rc) return rc;
+  if (k == 0) return accumulate ? 0 : launch_zero<float>(m, n, dC, ldc, st);
+  mode = resolve_f32_mode(mode);
+  const bool tma = tma_ok(dA, lda, dB, ldb, 4);
+  switch (mode) {
+    case B200_F32_STRICT:
+      if (tma) return launch_ffma(m, n, k, dA, lda, dB, ldb, dC, ldc, accumulate, st);
+      return launch_generic<float, float>(m, n, k, dA, lda, dB, ldb, dC, ldc, accumulate, st, "generic_f32_64x64");
+    case B200_F32_TF32:
+      if (accumulate) return B200_ERR_UNSUPPORTED;
+      if (!tma) return launch_generic<float, float>(m, n, k, dA, lda, dB, ldb, dC, ldc, 0, st, "generic_f32_64x64");
+      if (n <= 128)
+        return launch_tc<KIND_TF32, 128, 6, float>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, "tc_tf32_128x128");
+      return launch_tc<KIND_TF32, 256, 4, float>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, "tc_tf32_128x256");
+    default:
+      return B200_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200_gemm_version(void) { return "b200gemm 0.1 (sm_100a; tcgen05+TMA; round 1)"; }
+
+int b200_gemm_device_ok(void) { return ensure_device(); }
+
+const char* b200_gemm_strerror(int code) {
+  switch (code) {
+    case B200_OK: return "ok";
+    case B200_ERR_BAD_ARG: return "bad argument";
+    case B200_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (there is no CPU fallback)";
+    case B200_ERR_UNSUPPORTED: return "mode not supported for these operands";
+    case B200_ERR_TENSORMAP: return "cuTensorMapEncodeTiled failed";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown";
+  }
+}
+
+const char* b200_gemm_last_kernel(void) { return t_last_kernel; }
+unsigned long long b200_gemm_launch_count(void) { return g_launches.load(); }
+int b200_gemm_default_f32_mode(void) { return resolve_f32_mode(B200_F32_AUTO); }
+void b200_gemm_set_default_f32_mode(int mode) {
+  if (mode >= 0 && mode < B200_F32_AUTO) g_default_f32_mode.store(mode);
+}
+void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes) { g_dbg_b_lbo = lbo_bytes; g_dbg_b_sbo = sbo_bytes; }
+
+int b200_gemm_f32(int m, int n, int k, const float* dA, int lda, const float* dB, int ldb, float* dC,
+                  int ldc, int precision_mode, void* stream) {
+  return gemm_f32_impl(m, n, k, dA, lda, dB, ldb, dC, ldc, precision_mode, 0, (cudaStream_t)stream);
+}
+
+int b200_gemm_bf16(int m, int n, int k, const uint16_t* dA, int lda, const uint16_t* dB, int ldb,
+                   void* dC, int ldc, int out_type, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_type != B200_OUT_F32 && out_type != B200_OUT_BF16) return B200_ERR_BAD_ARG;
+  int rc = check_args(m, n, k, dA, lda, dB, ldb, dC, ldc);
+  if (rc == 1) return 0;
+  if (rc) return rc;
+  rc = ensure_device();
+  if (rc) return rc;
+  if (k == 0)
+    return out_type == B200_OUT_F32 ? launch_zero<float>(m, n, (float*)dC, ldc, st)
+                                    : launch_zero<uint16_t>(m, n, (uint16_t*)dC, ldc, st);
+  if (!tma_ok(dA, lda, dB, ldb, 2)) {
+    if (out_type == B200_OUT_F32)
+      return launch_generic<uint16_t, float>(m, n, k, dA, lda, dB, ldb, (float*)dC, ldc, 0, st, "generic_bf16_64x64");
+    return launch_generic<uint16_t, uint16_t>(m, n, k, dA, lda, dB, ldb, (uint16_t*)dC, ldc, 0, st, "generic_bf16_64x64");
+  }
+  if (out_type == B200_OUT_F32) {
+    if (n <= 128) return launch_tc<KIND_F16, 128, 6, float>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, "tc_bf16_128x128");
+    return launch_tc<KIND_F16, 256, 4, float>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, "tc_bf16_128x256");
+  }
+  if (n <= 128) return launch_tc<KIND_F16, 128, 6, bf16_out>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, "tc_bf16_128x128_obf16");
+  return launch_tc<KIND_F16, 256, 4, bf16_out>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, "tc_bf16_128x256_obf16");
+}
+
+int b200_gemm_s8s32(int m, int n, int k, const int8_t* dA, int lda, const int8_t* dB, int ldb,
+                    int32_t* dC, int ldc, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = check_args(m, n, k, dA, lda, dB, ldb, dC, ldc);
+  if (rc == 1) return 0;
+  if (rc) return rc;
+  rc = ensure_device();
+  if (rc) return rc;
+  if (k == 0) return launch_zero<int32_t>(m, n, dC, ldc, st);
+  if (!tma_ok(dA, lda, dB, ldb, 1))
+    return launch_generic<int8_t, int32_t>(m, n, k, dA, lda, dB, ldb, dC, ldc, 0, st, "generic_s8_64x64");
+  if (n <= 128) return launch_tc<KIND_I8, 128, 6, int32_t>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, "tc_s8_128x128");
+  return launch_tc<KIND_I8, 256, 4, int32_t>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, "tc_s8_128x256");
+}
+
+int b200_convert_f32_to_bf16(const float* dSrc, uint16_t* dDst, size_t count, void* stream) {
+  if (count == 0) return 0;
+  if (!dSrc || !dDst) return B200_ERR_BAD_ARG;
+  int rc = ensure_device();
+  if (rc) return rc;
+  size_t blocks = (count + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  convert_f32_to_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dSrc, dDst, count);
+  g_launches++;
+  t_last_kernel = "convert_f32_to_bf16";
+  return last_launch_status();
+}
+
+// ---- host-pointer entry points (plumbing / parity only) ----------------------------------------
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = (int)e_; goto done; } } while (0)
+
+int b200_gemm_f32_host(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C,
+                       int ldc, int precision_mode) {
+  int rc = check_args(m, n, k, A, lda, B, ldb, C, ldc);
+  if (rc == 1) return 0;
+  if (rc) return rc;
+  rc = ensure_device();
+  if (rc) return rc;
+  float *dA = nullptr, *dB = nullptr, *dC = nullptr, *dT = nullptr;
+  const int mode = resolve_f32_mode(precision_mode);
+  const size_t pa = (size_t)k * 4, pb = (size_t)n * 4, pc = (size_t)n * 4;   // packed device copies
+  if (k > 0) {
+    CK(cudaMalloc(&dA, pa * m));
+    CK(cudaMalloc(&dB, pb * k));
+    CK(cudaMemcpy2D(dA, pa, A, (size_t)lda * 4, pa, m, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy2D(dB, pb, B, (size_t)ldb * 4, pb, k, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMalloc(&dC, pc * m));
+  CK(cudaMemcpy2D(dC, pc, C, (size_t)ldc * 4, pc, m, cudaMemcpyHostToDevice));
+  if (mode == B200_F32_STRICT) {
+    rc = gemm_f32_impl(m, n, k, dA, k, dB, n, dC, n, mode, /*accumulate=*/1, 0);
+    if (rc) goto done;
+  } else {
+    CK(cudaMalloc(&dT, pc * m));
+    rc = gemm_f32_impl(m, n, k, dA, k, dB, n, dT, n, mode, 0, 0);
+    if (rc) goto done;
+    dim3 grid((n + 255) / 256, m < 4096 ? m : 4096);
+    add_inplace_kernel<float><<<grid, 256>>>(m, n, dC, n, dT, n);
+    g_launches++;
+    rc = last_launch_status();
+    if (rc) goto done;
+  }
+  CK(cudaMemcpy2D(C, (size_t)ldc * 4, dC, pc, pc, m, cudaMemcpyDeviceToHost));
+  CK(cudaDeviceSynchronize());
+done:
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dT);
+  return rc;
+}
+
+int b200_gemm_s8s32_host(int m, int n, int k, const int8_t* A, int lda, const int8_t* B, int ldb,
+                         int32_t* C, int ldc) {
+  int rc = check_args(m, n, k, A, lda, B, ldb, C, ldc);
+  if (rc == 1) return 0;
+  if (rc) return rc;
+  rc = ensure_device();
+  if (rc) return rc;
+  int8_t *dA = nullptr, *dB = nullptr;
+  int32_t* dC = nullptr;
+  // device copies padded to 16-byte pitches so the TMA path is taken for any m,n,k
+  const size_t pa = ((size_t)k + 15) & ~(size_t)15, pb = ((size_t)n + 15) & ~(size_t)15;
+  const size_t pc = (size_t)n * 4;
+  if (k > 0) {
+    CK(cudaMalloc(&dA, pa * m));
+    CK(cudaMalloc(&dB, pb * k));
+    CK(cudaMemcpy2D(dA, pa, A, (size_t)lda, (size_t)k, m, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy2D(dB, pb, B, (size_t)ldb, (size_t)n, k, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMalloc(&dC, pc * m));
+  rc = b200_gemm_s8s32(m, n, k, dA, (int)pa, dB, (int)pb, dC, n, nullptr);
+  if (rc) goto done;
+  CK(cudaMemcpy2D(C, (size_t)ldc * 4, dC, pc, pc, m, cudaMemcpyDeviceToHost));
+  CK(cudaDeviceSynchronize());
+done:
+  cudaFree(dA); cudaFree(dB); cudaFree(dC);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,285 @@
+// gemm_tc.cuh — the tensor-core path: persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[m x n] = A[m x k] * B[k x n],  all row-major.
+//
+// Mapping of the reference's roles onto Blackwell:
+//   packA / packB  (aarch64/MMult_4x4_21.cpp:459-572; the gmem->smem staging of
+//                   cuda/MMult_cuda_12.cu:113-198)      -> TMA bulk-tensor copies with 128B swizzle
+//                                                          into a STAGES-deep shared-memory ring
+//   4x4 / 8x12 register micro-kernel (kernel_8x12,
+//                   cuda/MMult_cuda_12.cu:200-206)      -> one thread issuing tcgen05.mma 128 x BN x K16
+//                                                          into a TMEM accumulator (fp32 / int32)
+//   stg128 epilogue (cuda/MMult_cuda_12.cu:210-222)     -> tcgen05.ld -> swizzled smem transpose ->
+//                                                          coalesced 16-byte st.global
+//
+// Row-major B is the MMA's "MN-major" operand: no transpose pass (the job of reorder_b / trans_w in
+// aarch64-int8/MMult_4x8_21.c:45-71) exists here; TMA drops [BK x 128B] column blocks of B straight
+// into the canonical MN-major SWIZZLE_128B layout and the descriptor walks them (LBO = block stride).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
+// warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).  Three pipelines: smem full/empty,
+// TMEM full/empty (two accumulator stages, so the epilogue of tile i overlaps the mainloop of i+1),
+// and the static persistent tile schedule.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200 {
+
+template <int KIND> struct KindTraits;
+template <> struct KindTraits<KIND_F16>  { static constexpr int ELEM = 2, UMMA_K = 16, AB_FMT = 1, C_FMT = 1; };
+template <> struct KindTraits<KIND_TF32> { static constexpr int ELEM = 4, UMMA_K = 8,  AB_FMT = 2, C_FMT = 1; };
+template <> struct KindTraits<KIND_I8>   { static constexpr int ELEM = 1, UMMA_K = 32, AB_FMT = 1, C_FMT = 2; };
+
+struct TcParams {
+  void* C;
+  long long ldc;           // elements
+  int M, N, K;
+  int tiles_m, tiles_n;
+  int group_m;             // rasterisation: tiles are walked m-fastest inside groups of group_m rows
+  int vec_ok;              // C base and ldc allow 16-byte stores
+  int dbg_b_lbo, dbg_b_sbo;  // 0 = defaults (probe hook, see b200_gemm_debug_set_b_desc)
+};
+
+template <int KIND, int BN, int STAGES>
+struct TcConfig {
+  using T = KindTraits<KIND>;
+  static constexpr int BM = 128;
+  static constexpr int BK = 128 / T::ELEM;                 // one 128B swizzle row of K per stage
+  static constexpr int A_STAGE = BM * 128;                 // 16 KB
+  static constexpr int B_BOX_COLS = 128 / T::ELEM;         // elements per 128B-wide column block
+  static constexpr int B_BOXES = BN / B_BOX_COLS;
+  static constexpr int B_BOX_BYTES = BK * 128;
+  static constexpr int B_STAGE = B_BOXES * B_BOX_BYTES;    // = BN * 128
+  static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
+  static constexpr int MMAS_PER_STAGE = BK / T::UMMA_K;    // 4 for every kind
+  static constexpr int A_KADV = T::UMMA_K * T::ELEM;       // 32 B inside the swizzled row
+  static constexpr int B_KADV = T::UMMA_K * 128;           // UMMA_K k-rows of 128 B
+  static constexpr int EPI_STAGING = 4 * 32 * 128;         // 4 warps x 32 rows x 128 B
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_STAGING +
+                                    NUM_BARS * 8 + 16;
+  static constexpr int THREADS = 192;
+};
+
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int group_m, int& mb,
+                                            int& nb) {
+  const int per_group = group_m * tiles_n;
+  const int g = t / per_group;
+  const int first_m = g * group_m;
+  const int rows = min(group_m, tiles_m - first_m);
+  const int r = t - g * per_group;
+  mb = first_m + r % rows;
+  nb = r / rows;
+}
+
+template <typename OutT> struct OutPack;
+template <> struct OutPack<float> {
+  static constexpr int COLS = 32;   // accumulator columns per 128-byte staging row
+  __device__ static void pack(const uint32_t (&a)[32], const uint32_t (&)[32], uint32_t (&w)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; i++) w[i] = a[i];
+  }
+};
+template <> struct OutPack<int32_t> {
+  static constexpr int COLS = 32;
+  __device__ static void pack(const uint32_t (&a)[32], const uint32_t (&)[32], uint32_t (&w)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; i++) w[i] = a[i];
+  }
+};
+struct bf16_out {};   // tag: C stored as bf16 (RNE from the fp32 accumulator)
+template <> struct OutPack<bf16_out> {
+  static constexpr int COLS = 64;
+  __device__ static uint32_t cvt2(uint32_t lo, uint32_t hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+    return r;
+  }
+  __device__ static void pack(const uint32_t (&a)[32], const uint32_t (&b)[32], uint32_t (&w)[32]) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = cvt2(a[2 * i], a[2 * i + 1]);
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[16 + i] = cvt2(b[2 * i], b[2 * i + 1]);
+  }
+};
+template <typename OutT> struct OutBytes { static constexpr int V = 4; };
+template <> struct OutBytes<bf16_out> { static constexpr int V = 2; };
+
+template <int KIND, int BN, int STAGES, typename OutT>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcParams p) {
+  using Cfg = TcConfig<KIND, BN, STAGES>;
+  using T = KindTraits<KIND>;
+  constexpr int OB = OutBytes<OutT>::V;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1 KB
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + STAGES * Cfg::A_STAGE;
+  const uint32_t sEpi = sB + STAGES * Cfg::B_STAGE;
+  const uint32_t sBar = sEpi + Cfg::EPI_STAGING;
+  const uint32_t bar_full = sBar;
+  const uint32_t bar_empty = sBar + 8 * STAGES;
+  const uint32_t bar_tfull = sBar + 16 * STAGES;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  const uint32_t s_tmem_ptr = bar_tempty + 16;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; i++) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(s_tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (s_tmem_ptr - smem_base));
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_kb = (p.K + Cfg::BK - 1) / Cfg::BK;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int mb, nb;
+        tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, mb, nb);
+        const int m0 = mb * Cfg::BM, n0 = nb * BN;
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t full = bar_full + 8 * s;
+          mbar_arrive_expect_tx(full, Cfg::STAGE_BYTES);
+          tma_load_2d(sA + s * Cfg::A_STAGE, &tmA, full, kb * Cfg::BK, m0);
+#pragma unroll
+          for (int j = 0; j < Cfg::B_BOXES; j++)
+            tma_load_2d(sB + s * Cfg::B_STAGE + j * Cfg::B_BOX_BYTES, &tmB, full,
+                        n0 + j * Cfg::B_BOX_COLS, kb * Cfg::BK);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(T::C_FMT, T::AB_FMT, /*a_mn=*/0, /*b_mn=*/1, 128, BN);
+      const uint32_t b_lbo = p.dbg_b_lbo ? (uint32_t)p.dbg_b_lbo : (uint32_t)Cfg::B_BOX_BYTES;
+      const uint32_t b_sbo = p.dbg_b_sbo ? (uint32_t)p.dbg_b_sbo : 1024u;
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t a0 = sA + s * Cfg::A_STAGE;
+          const uint32_t b0 = sB + s * Cfg::B_STAGE;
+#pragma unroll
+          for (int k = 0; k < Cfg::MMAS_PER_STAGE; k++) {
+            const uint64_t ad = make_sdesc(a0 + k * Cfg::A_KADV, 16, 1024);
+            const uint64_t bd = make_sdesc(b0 + k * Cfg::B_KADV, b_lbo, b_sbo);
+            tc_mma<KIND>(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(bar_empty + 8 * s);            // frees the smem slot when these MMAs retire
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        tc_commit(bar_tfull + 8 * as);              // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps) =====================
+    const int q = warp & 3;                          // TMEM lane quadrant this warp may read
+    uint8_t* stg = smem_gen + (sEpi - smem_base) + q * 4096;   // 32 rows x 128 B, chunk-swizzled
+    constexpr int COLS = OutPack<OutT>::COLS;
+    constexpr int PASSES = BN / COLS;
+    constexpr int VEC_ELEMS = 16 / OB;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int mb, nb;
+      tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, mb, nb);
+      const int m0 = mb * Cfg::BM + q * 32, n0 = nb * BN;
+      mbar_wait(bar_tfull + 8 * as, aph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int ps = 0; ps < PASSES; ps++) {
+        uint32_t ra[32], rb[32], w[32];
+        tmem_ld_32x32b_x32(t_addr + ps * (COLS == 64 ? 64 : 32), ra);
+        if constexpr (COLS == 64) tmem_ld_32x32b_x32(t_addr + ps * 64 + 32, rb);
+        tmem_ld_wait();
+        if (ps == PASSES - 1) {                      // TMEM stage fully drained: hand it back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+        }
+        OutPack<OutT>::pack(ra, rb, w);
+        // registers (row = lane) -> staging, 16-byte chunk index XOR (row & 7): conflict-free both ways
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          uint4 v = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
+        }
+        __syncwarp();
+        // staging -> global: 8 lanes cover one 128-byte row segment, 4 rows per instruction
+        const int chunk = lane & 7;
+        const int col = n0 + ps * COLS + chunk * VEC_ELEMS;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int row = i * 4 + (lane >> 3);
+          const int gm = m0 + row;
+          uint4 v = *reinterpret_cast<const uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4));
+          if (gm < p.M) {
+            uint8_t* dst = reinterpret_cast<uint8_t*>(p.C) + ((long long)gm * p.ldc + col) * OB;
+            if (p.vec_ok && col + VEC_ELEMS <= p.N) {
+              *reinterpret_cast<uint4*>(dst) = v;
+            } else {
+              const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+              if constexpr (OB == 4) {
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                  if (col + e < p.N) reinterpret_cast<uint32_t*>(dst)[e] = vv[e];
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; e++)
+                  if (col + e < p.N)
+                    reinterpret_cast<uint16_t*>(dst)[e] = (uint16_t)(vv[e >> 1] >> ((e & 1) * 16));
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace b200
