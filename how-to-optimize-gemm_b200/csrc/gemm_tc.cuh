@@ -26,9 +26,13 @@
 namespace b200 {
 
 template <int KIND> struct KindTraits;
-template <> struct KindTraits<KIND_F16>  { static constexpr int ELEM = 2, UMMA_K = 16, AB_FMT = 1, C_FMT = 1; };
-template <> struct KindTraits<KIND_TF32> { static constexpr int ELEM = 4, UMMA_K = 8,  AB_FMT = 2, C_FMT = 1; };
-template <> struct KindTraits<KIND_I8>   { static constexpr int ELEM = 1, UMMA_K = 32, AB_FMT = 1, C_FMT = 2; };
+// B_LAYOUT / B_SBO: MN-major B uses SWIZZLE_128B (8 k-rows of 128 B per atom, SBO 1024) except for
+// 32-bit elements, where the only MN-major layout the tensor core accepts is SWIZZLE_128B_BASE32B
+// (32-byte swizzle granules, 4 k-rows per atom, SBO 512; TMA side CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+// Measured on B200: the 16-byte-atom layout with kind::tf32 returns all-zero accumulators.
+template <> struct KindTraits<KIND_F16>  { static constexpr int ELEM = 2, UMMA_K = 16, AB_FMT = 1, C_FMT = 1, B_LAYOUT = 2, B_SBO = 1024; };
+template <> struct KindTraits<KIND_TF32> { static constexpr int ELEM = 4, UMMA_K = 8,  AB_FMT = 2, C_FMT = 1, B_LAYOUT = 1, B_SBO = 512; };
+template <> struct KindTraits<KIND_I8>   { static constexpr int ELEM = 1, UMMA_K = 32, AB_FMT = 1, C_FMT = 2, B_LAYOUT = 2, B_SBO = 1024; };
 
 struct TcParams {
   void* C;
@@ -179,7 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(T::C_FMT, T::AB_FMT, /*a_mn=*/0, /*b_mn=*/1, 128, BN);
       const uint32_t b_lbo = p.dbg_b_lbo ? (uint32_t)p.dbg_b_lbo : (uint32_t)Cfg::B_BOX_BYTES;
-      const uint32_t b_sbo = p.dbg_b_sbo ? (uint32_t)p.dbg_b_sbo : 1024u;
+      const uint32_t b_sbo = p.dbg_b_sbo ? (uint32_t)p.dbg_b_sbo : (uint32_t)T::B_SBO;
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -196,7 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < Cfg::MMAS_PER_STAGE; k++) {
             const uint64_t ad = make_sdesc(a0 + k * Cfg::A_KADV, 16, 1024);
-            const uint64_t bd = make_sdesc(b0 + k * Cfg::B_KADV, b_lbo, b_sbo);
+            const uint64_t bd = make_sdesc(b0 + k * Cfg::B_KADV, b_lbo, b_sbo, T::B_LAYOUT);
             tc_mma<KIND>(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           tc_commit(bar_empty + 8 * s);            // frees the smem slot when these MMAs retire

@@ -1,0 +1,220 @@
+"""Parity tests proper (-m gpu): the CUDA path through the C ABI against the oracle, the committed
+golden vectors of the reference, and size-independent properties at BASELINE.json's full sizes.
+
+Bars: bit-exact for int8->int32 and for the strict fp32 path (sequential-k FFMA == the reference's
+naive REF_MMult as its own flags build it); tensor-core fp32/bf16 within the north_star tolerance
+1e-3 * max|Cref| (tightened per mode below)."""
+import os
+
+import numpy as np
+import pytest
+
+import _libs
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+TOL_TF32 = 1e-3     # north_star: within 1e-3 max relative error of REF_MMult
+TOL_BF16 = 2e-5     # bf16-rounded inputs, fp32 accumulate: only accumulation-order noise remains
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rel(c, t):
+    return float(np.abs(c.astype(np.float64) - t).max() / max(np.abs(t).max(), 1e-30))
+
+
+SHAPES = [(1, 1, 1), (4, 4, 4), (7, 9, 5), (64, 48, 80), (77, 77, 77), (128, 128, 128), (128, 256, 64),
+          (130, 70, 257), (256, 384, 512), (300, 260, 100), (1, 1000, 333), (1000, 1, 77), (513, 1027, 260)]
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES)
+def test_f32_strict_bit_exact(gemm, oracle, m, n, k):
+    a, b = _libs.gen_f32(oracle, m, k, 21), _libs.gen_f32(oracle, k, n, 22)
+    c = gemm.gemm_f32(cuda(a), cuda(b), mode=gemm.F32_STRICT).cpu().numpy()
+    assert np.array_equal(c, _libs.ref_f32_fma(oracle, a, b)), gemm.last_kernel()
+
+
+@pytest.mark.parametrize("pad_a,pad_b,pad_c", [(0, 0, 0), (4, 8, 12), (1, 0, 0), (0, 3, 0), (0, 0, 5), (3, 5, 7)])
+def test_f32_strict_leading_dimensions(gemm, oracle, pad_a, pad_b, pad_c):
+    """lda/ldb/ldc != k/n/n: the reference never exercises these (cuda/test_MMult.cpp:62) and its
+    kernels ignore them; the C ABI honours them, aligned (TMA) or not (generic kernel)."""
+    m, n, k = 200, 136, 264
+    A = cuda(_libs.gen_f32(oracle, m, k + pad_a, 1))[:, :k]
+    B = cuda(_libs.gen_f32(oracle, k, n + pad_b, 2))[:, :n]
+    Cbuf = torch.full((m, n + pad_c), -7.0, device="cuda")
+    gemm.gemm_f32(A, B, out=Cbuf[:, :n], mode=gemm.F32_STRICT)
+    ref = _libs.ref_f32_fma(oracle, A.cpu().numpy(), B.cpu().numpy())
+    assert np.array_equal(Cbuf[:, :n].cpu().numpy(), ref), gemm.last_kernel()
+    if pad_c:
+        assert (Cbuf[:, n:] == -7.0).all(), "wrote outside the m x n window"
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES)
+def test_f32_tf32_within_tolerance(gemm, oracle, m, n, k):
+    a, b = _libs.gen_f32(oracle, m, k, 23), _libs.gen_f32(oracle, k, n, 24)
+    c = gemm.gemm_f32(cuda(a), cuda(b), mode=gemm.F32_TF32).cpu().numpy()
+    t = _libs.ref_f64(oracle, a, b)
+    assert rel(c, t) <= TOL_TF32, (gemm.last_kernel(), rel(c, t))
+    # and under the reference harness's own gate (cuda/test_MMult.cpp:124)
+    assert np.abs(c - _libs.ref_f32_fma(oracle, a, b)).max() < 0.5
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES)
+@pytest.mark.parametrize("out", ["f32", "bf16"])
+def test_bf16(gemm, oracle, m, n, k, out):
+    a = _libs.round_bf16(oracle, _libs.gen_f32(oracle, m, k, 25))
+    b = _libs.round_bf16(oracle, _libs.gen_f32(oracle, k, n, 26))
+    od = torch.float32 if out == "f32" else torch.bfloat16
+    c = gemm.gemm_bf16(cuda(a).bfloat16(), cuda(b).bfloat16(), out_dtype=od).float().cpu().numpy()
+    t = _libs.ref_f64(oracle, a, b)
+    if out == "f32":
+        assert rel(c, t) <= TOL_BF16, (gemm.last_kernel(), rel(c, t))
+    else:   # one RNE rounding of the fp32 accumulator to bf16: half an ulp = 2^-9 relative, elementwise
+        assert np.all(np.abs(c - t) <= np.abs(t) * 2.0 ** -8 + TOL_BF16 * np.abs(t).max())
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES + [(128, 256, 4096), (33, 47, 1000)])
+def test_s8s32_bit_exact(gemm, oracle, m, n, k):
+    a, b = _libs.gen_s8(oracle, m, k, 27), _libs.gen_s8(oracle, k, n, 28)
+    c = gemm.gemm_s8s32(cuda(a), cuda(b)).cpu().numpy()
+    assert np.array_equal(c, _libs.ref_s8(oracle, a, b)), gemm.last_kernel()
+
+
+def test_s8_extremes_and_alignment(gemm, oracle):
+    """[-127,127] extremes (chgemm input contract, /root/reference/README.md:82); 16-byte aligned
+    pitches go through tcgen05 kind::i8, everything else through the CUDA-core kernel: same bits."""
+    m, n, k = 160, 272, 512
+    for fill_a, fill_b in [(127, 127), (-127, 127), (-127, -127)]:
+        a = np.full((m, k), fill_a, np.int8)
+        b = np.full((k, n), fill_b, np.int8)
+        c = gemm.gemm_s8s32(cuda(a), cuda(b)).cpu().numpy()
+        assert gemm.last_kernel().startswith("tc_s8")
+        assert (c == fill_a * fill_b * k).all()
+    a, b = _libs.gen_s8(oracle, m, k + 16, 1), _libs.gen_s8(oracle, k, n + 16, 2)
+    A, B = cuda(a), cuda(b)
+    c_tc = gemm.gemm_s8s32(A[:, :k], B[:, :n]).cpu().numpy()
+    k_tc = gemm.last_kernel()
+    c_cc = gemm.gemm_s8s32(A[:, 1:k + 1], B[1:k + 1, 1:n + 1]).cpu().numpy()   # misaligned bases
+    assert k_tc.startswith("tc_s8") and gemm.last_kernel().startswith("generic_s8")
+    assert np.array_equal(c_tc, _libs.ref_s8(oracle, a[:, :k], b[:, :n]))
+    assert np.array_equal(c_cc, _libs.ref_s8(oracle, a[:, 1:k + 1], b[1:k + 1, 1:n + 1]))
+
+
+def test_empty_and_k_zero(gemm):
+    A = torch.zeros((0, 8), device="cuda")
+    B = torch.zeros((8, 5), device="cuda")
+    assert gemm.gemm_f32(A, B, mode=gemm.F32_STRICT).shape == (0, 5)
+    C = torch.full((6, 5), 3.0, device="cuda")
+    gemm.gemm_f32(torch.zeros((6, 0), device="cuda"), torch.zeros((0, 5), device="cuda"), out=C, mode=gemm.F32_STRICT)
+    assert (C == 0).all()      # C = A*B with k = 0 is the zero matrix
+    Ci = torch.full((6, 5), 3, device="cuda", dtype=torch.int32)
+    gemm.gemm_s8s32(torch.zeros((6, 0), device="cuda", dtype=torch.int8), torch.zeros((0, 5), device="cuda", dtype=torch.int8), out=Ci)
+    assert (Ci == 0).all()
+
+
+# ---- the reference's golden vectors, through the C ABI -------------------------------------------
+@pytest.mark.parametrize("idx", sorted({k.split("_")[1] for k in G.files if k.startswith("f32_")}))
+def test_golden_f32(gemm, idx):
+    a, b = G[f"f32_{idx}_a"], G[f"f32_{idx}_b"]
+    c = gemm.gemm_f32(cuda(a), cuda(b), mode=gemm.F32_STRICT).cpu().numpy()
+    assert np.array_equal(c, G[f"f32_{idx}_c_naive"])                 # reference's naive REF_MMult: bit-exact
+    assert np.abs(c - G[f"f32_{idx}_c_openblas"]).max() < 1e-4        # reference's OpenBLAS REF_MMult
+    c = gemm.gemm_f32(cuda(a), cuda(b), mode=gemm.F32_TF32).cpu().numpy()
+    assert np.abs(c - G[f"f32_{idx}_c_openblas"]).max() <= TOL_TF32 * np.abs(G[f"f32_{idx}_c_openblas"]).max()
+
+
+def test_golden_ones(gemm):
+    a, b, cref = G["ones_a"], G["ones_b"], G["ones_c"]
+    for mode in (gemm.F32_STRICT, gemm.F32_TF32):
+        assert np.array_equal(gemm.gemm_f32(cuda(a), cuda(b), mode=mode).cpu().numpy(), cref)
+    assert np.array_equal(gemm.gemm_bf16(cuda(a).bfloat16(), cuda(b).bfloat16()).cpu().numpy(), cref)
+
+
+@pytest.mark.parametrize("idx", sorted({k.split("_")[1] for k in G.files if k.startswith("s8_")}))
+def test_golden_s8(gemm, idx):
+    a, b, cref = G[f"s8_{idx}_a"], G[f"s8_{idx}_b"], G[f"s8_{idx}_c"]
+    assert np.array_equal(gemm.gemm_s8s32(cuda(a), cuda(b)).cpu().numpy(), cref)
+    c = np.zeros_like(cref)
+    gemm.MY_MMult_int8(a.shape[0], b.shape[1], a.shape[1], a, a.shape[1], b, b.shape[1], c, b.shape[1])
+    assert np.array_equal(c, cref)          # host entry = what aarch64-int8/test_MMult.c:98 calls
+
+
+# ---- host entry points: the CPU harness contract C += A*B ----------------------------------------
+def test_host_entry_accumulates(gemm, oracle):
+    m, n, k = 96, 80, 160
+    a, b, c0 = _libs.gen_f32(oracle, m, k, 1), _libs.gen_f32(oracle, k, n, 2), _libs.gen_f32(oracle, m, n, 3)
+    c = c0.copy()
+    gemm.MY_MMult(m, n, k, a, k, b, n, c, n, mode=gemm.F32_STRICT)
+    assert np.array_equal(c, _libs.ref_f32_fma(oracle, a, b, c0))
+    c = c0.copy()
+    gemm.MY_MMult(m, n, k, a, k, b, n, c, n, mode=gemm.F32_TF32)
+    t = _libs.ref_f64(oracle, a, b) + c0
+    assert rel(c, t) <= TOL_TF32
+
+
+# ---- BASELINE.json full sizes: size-independent properties ---------------------------------------
+@pytest.mark.parametrize("N", [4096])
+def test_full_size_properties_f32(gemm, oracle, N):
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.rand((N, N), device="cuda", generator=gen) * 2 - 1
+    B = torch.rand((N, N), device="cuda", generator=gen) * 2 - 1
+    # (1) all-ones fixture of the aarch64 harness: every element == K exactly, every mode
+    ones = torch.ones((N, N), device="cuda")
+    for mode in (gemm.F32_STRICT, gemm.F32_TF32):
+        assert (gemm.gemm_f32(ones, ones, mode=mode) == N).all()
+    # (2) row subset against the oracle: strict is bit-exact, tf32 within tolerance
+    rows = torch.arange(0, N, 61, device="cuda")[:64]
+    a_np, b_np = A[rows].cpu().numpy(), B.cpu().numpy()
+    ref = _libs.ref_f32_fma(oracle, a_np, b_np)
+    Cs = gemm.gemm_f32(A, B, mode=gemm.F32_STRICT)
+    assert np.array_equal(Cs[rows].cpu().numpy(), ref)
+    Ct = gemm.gemm_f32(A, B, mode=gemm.F32_TF32)
+    t = _libs.ref_f64(oracle, a_np, b_np)
+    assert rel(Ct[rows].cpu().numpy(), t) <= TOL_TF32
+    # (3) whole-matrix agreement of the two independent GPU paths (catches tile-scheduling holes)
+    assert float((Cs - Ct).abs().max() / Cs.abs().max()) <= TOL_TF32
+    # (4) linearity in A, exact for power-of-two scaling
+    assert torch.equal(gemm.gemm_f32(A * 2, B, mode=gemm.F32_TF32), Ct * 2)
+    # (5) checksum of checksums: sum_j C(i,j) == A(i,:) . rowsum(B)   (fp64 on device)
+    lhs = Cs.double().sum(dim=1)
+    rhs = A.double() @ B.double().sum(dim=1)
+    assert float((lhs - rhs).abs().max()) <= 1e-3 * float(rhs.abs().max()) + 1e-2
+
+
+@pytest.mark.parametrize("N", [4096, 8192])
+def test_full_size_properties_bf16(gemm, oracle, N):
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    A = (torch.rand((N, N), device="cuda", generator=gen) * 2 - 1).bfloat16()
+    B = (torch.rand((N, N), device="cuda", generator=gen) * 2 - 1).bfloat16()
+    C = gemm.gemm_bf16(A, B)
+    rows = torch.arange(0, N, 127, device="cuda")[:32]
+    t = _libs.ref_f64(oracle, A[rows].float().cpu().numpy(), B.float().cpu().numpy())
+    assert rel(C[rows].cpu().numpy(), t) <= TOL_BF16
+    ones = torch.ones((N, N), device="cuda", dtype=torch.bfloat16)
+    assert (gemm.gemm_bf16(ones, ones) == N).all()
+    lhs = C.double().sum(dim=1)
+    rhs = A.double() @ B.double().sum(dim=1)
+    assert float((lhs - rhs).abs().max()) <= 1e-4 * float(rhs.abs().max()) + 1e-2
+
+
+def test_full_size_s8_4096(gemm, oracle):
+    N = 4096
+    a, b = _libs.gen_s8(oracle, N, N, 31), _libs.gen_s8(oracle, N, N, 32)
+    A, B = cuda(a), cuda(b)
+    C = gemm.gemm_s8s32(A, B)
+    assert gemm.last_kernel().startswith("tc_s8")
+    rows = np.arange(0, N, 29)[:128]
+    assert np.array_equal(C[torch.from_numpy(rows).cuda()].cpu().numpy(), _libs.ref_s8(oracle, a[rows], b))
+    # exact integer identity over the WHOLE matrix: row sums of C == A . rowsum(B) in int64
+    lhs = C.long().sum(dim=1)
+    rhs = (A.double() @ B.double().sum(dim=1, keepdim=True)).squeeze(1).long()   # < 2^53: exact
+    assert torch.equal(lhs, rhs)
+    # the reference's ramp fixture at full size (values {0,1,2})
+    ar = np.zeros((N, N), np.int8)
+    oracle.oracle_random_int8_ramp(N, N, _libs.P(ar), N)
+    Cr = gemm.gemm_s8s32(cuda(ar), cuda(ar))
+    assert np.array_equal(Cr[:64].cpu().numpy(), _libs.ref_s8(oracle, ar[:64], ar))
