@@ -55,14 +55,14 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-i", str(self.index), "-lms", "10"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)
+        time.sleep(0.03)
         self.proc.terminate()
         self.proc.wait()
         self.f.close()
@@ -173,7 +173,7 @@ def cpu_baseline(o, budget_s=12.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--mode", type=int, default=-1, help="fp32 precision mode of the headline (default: library default)")

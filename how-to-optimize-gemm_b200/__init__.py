@@ -23,7 +23,8 @@ EXPORTS = [
     "b200_gemm_version", "b200_gemm_device_ok", "b200_gemm_strerror", "b200_gemm_last_kernel",
     "b200_gemm_launch_count", "b200_gemm_default_f32_mode", "b200_gemm_set_default_f32_mode",
     "b200_gemm_f32", "b200_gemm_f32_host", "b200_gemm_bf16", "b200_gemm_s8s32",
-    "b200_gemm_s8s32_host", "b200_convert_f32_to_bf16", "b200_gemm_debug_set_b_desc",
+    "b200_gemm_s8s32_host", "b200_convert_f32_to_bf16", "b200_gemm_debug_set_b_desc", "b200_gemm_debug_set_bn",
+    "b200_gemm_debug_set_split_chunk",
 ]
 
 
@@ -53,6 +54,8 @@ lib.b200_gemm_s8s32_host.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i]
 lib.b200_convert_f32_to_bf16.argtypes = [_vp, _vp, C.c_size_t, _vp]
 lib.b200_gemm_debug_set_b_desc.argtypes = [_i, _i]
 lib.b200_gemm_set_default_f32_mode.argtypes = [_i]
+lib.b200_gemm_debug_set_bn.argtypes = [_i]
+lib.b200_gemm_debug_set_split_chunk.argtypes = [_i, _i]
 
 
 def _check(rc):

@@ -85,7 +85,7 @@ constexpr size_t kMapCache = 64;
 // 2-D row-major tensor: dim0 (inner, contiguous) x dim1 rows with pitch ld_bytes.
 int get_map(CUtensorMap* out, const void* ptr, CUtensorMapDataType dt, int elem_bytes,
             unsigned long long inner, unsigned long long rows, unsigned long long ld_bytes,
-            unsigned box_inner, unsigned box_rows, int swizzle /*0 none, 1 = 128B, 2 = 128B atom 32B*/) {
+            unsigned box_inner, unsigned box_rows, int swizzle /*0 none, 1 = 128B, 2 = 128B atom 32B, 3 = 64B*/) {
   MapKey key{ptr, (int)dt, inner, rows, ld_bytes, box_inner, box_rows, swizzle, g_dev.dev};
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto& e : g_maps)
@@ -98,7 +98,8 @@ int get_map(CUtensorMap* out, const void* ptr, CUtensorMapDataType dt, int elem_
   CUresult r = g_encode(&m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE,
                         swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
-                        : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                        : swizzle == 3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   (void)elem_bytes;
   if (r != CUDA_SUCCESS) return B200_ERR_TENSORMAP;
@@ -144,18 +145,22 @@ int launch_generic(int m, int n, int k, const InT* A, int lda, const InT* B, int
 }
 
 // ---- tensor-core launch -------------------------------------------------------------------
-template <int KIND, int BN, int STAGES, typename OutT>
-int launch_tc(int m, int n, int k, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
-              cudaStream_t st, const char* name) {
-  using Cfg = TcConfig<KIND, BN, STAGES>;
+int g_force_bn = 0;          // test/tuning hook (B200GEMM_BN or b200_gemm_debug_set_bn): 0 = heuristic
+
+template <int KIND, int BN, int STAGES, typename OutT, class Prod = ProdSingle, int A_ROW_BYTES = 128>
+int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_total, int a_plane_rows,
+              const void* B, long long ldb, int b_rows_total, int b_plane_rows, void* C, int ldc,
+              cudaStream_t st, const char* name, int chunk_k = 0) {
+  using Cfg = TcConfig<KIND, BN, STAGES, Prod, A_ROW_BYTES>;
   using T = KindTraits<KIND>;
   constexpr CUtensorMapDataType dt = KIND == KIND_F16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                    : KIND == KIND_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                                        : CU_TENSOR_MAP_DATA_TYPE_UINT8;
   CUtensorMap tmA, tmB;
-  int rc = get_map(&tmA, A, dt, T::ELEM, k, m, (unsigned long long)lda * T::ELEM, Cfg::BK, Cfg::BM, 1);
+  int rc = get_map(&tmA, A, dt, T::ELEM, k, a_rows_total, (unsigned long long)lda * T::ELEM, Cfg::BK, Cfg::BM,
+                   A_ROW_BYTES == 128 ? 1 : 3);
   if (rc) return rc;
-  rc = get_map(&tmB, B, dt, T::ELEM, n, k, (unsigned long long)ldb * T::ELEM, Cfg::B_BOX_COLS, Cfg::BK,
+  rc = get_map(&tmB, B, dt, T::ELEM, n, b_rows_total, (unsigned long long)ldb * T::ELEM, Cfg::B_BOX_COLS, Cfg::BK,
                T::B_LAYOUT == 1 ? 2 : 1);
   if (rc) return rc;
   TcParams p;
@@ -165,8 +170,11 @@ int launch_tc(int m, int n, int k, const void* A, int lda, const void* B, int ld
   p.group_m = 16;
   constexpr int OB = OutBytes<OutT>::V;
   p.vec_ok = aligned16(C) && ((long long)ldc * OB) % 16 == 0;
+  p.a_plane_rows = a_plane_rows; p.b_plane_rows = b_plane_rows;
+  p.chunk_kb = chunk_k > 0 ? (chunk_k + Cfg::BK - 1) / Cfg::BK : (k + Cfg::BK - 1) / Cfg::BK;
+  if (p.chunk_kb < 1) p.chunk_kb = 1;
   p.dbg_b_lbo = g_dbg_b_lbo; p.dbg_b_sbo = g_dbg_b_sbo;
-  auto kern = gemm_tc_kernel<KIND, BN, STAGES, OutT>;
+  auto kern = gemm_tc_kernel<KIND, BN, STAGES, OutT, Prod, A_ROW_BYTES>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -179,6 +187,99 @@ int launch_tc(int m, int n, int k, const void* A, int lda, const void* B, int ld
   g_launches++;
   t_last_kernel = name;
   return last_launch_status();
+}
+
+// Tile width: fewest "wave x tile-time" units over the persistent grid (tile time ~ BN plus a
+// fixed per-tile cost); 128 x 256 has the best operand reuse, narrower tiles quantise better.
+int pick_bn(int m, int n, bool allow256, bool allow192 = true) {
+  if (g_force_bn == 128 || (g_force_bn == 192 && allow192) || (g_force_bn == 256 && allow256)) return g_force_bn;
+  const int cands[3] = {256, 192, 128};
+  // relative MMA efficiency, measured on B200 at N=4096 (bf16: 1358 / 1230 / 864 TFLOP/s): the
+  // 1-CTA kernel is bound by shared-memory operand reads, which narrower tiles amortise worse
+  const double eff[3] = {1.00, 0.88, 0.62};
+  int best = 128;
+  double best_cost = 1e300;
+  const int tm = (m + 127) / 128;
+  for (int i = 0; i < 3; i++) {
+    if (cands[i] == 256 && !allow256) continue;
+    if (cands[i] == 192 && !allow192) continue;
+    const long long tiles = (long long)tm * ((n + cands[i] - 1) / cands[i]);
+    const long long waves = (tiles + g_dev.sms - 1) / g_dev.sms;
+    const double cost = (double)waves * (cands[i] / eff[i] + 8.0);
+    if (cost < best_cost) { best_cost = cost; best = cands[i]; }
+  }
+  return best;
+}
+
+#define TC_PLAIN(KIND, OUT, NAME)                                                                     \
+  switch (pick_bn(m, n, true)) {                                                                      \
+    case 256: return launch_tc<KIND, 256, 4, OUT>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, NAME "_128x256"); \
+    case 192: return launch_tc<KIND, 192, 5, OUT>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, NAME "_128x192"); \
+    default:  return launch_tc<KIND, 128, 6, OUT>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, NAME "_128x128"); \
+  }
+
+int tc_tf32(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C, int ldc, cudaStream_t st) {
+  TC_PLAIN(KIND_TF32, float, "tc_tf32")
+}
+int tc_bf16_f32(int m, int n, int k, const void* A, int lda, const void* B, int ldb, void* C, int ldc, cudaStream_t st) {
+  TC_PLAIN(KIND_F16, float, "tc_bf16")
+}
+int tc_bf16_bf16(int m, int n, int k, const void* A, int lda, const void* B, int ldb, void* C, int ldc, cudaStream_t st) {
+  TC_PLAIN(KIND_F16, bf16_out, "tc_bf16_obf16")
+}
+int tc_s8(int m, int n, int k, const void* A, int lda, const void* B, int ldb, void* C, int ldc, cudaStream_t st) {
+  // int8 column blocks are 128 elements wide (128 B): BN = 192 is not a whole number of them
+  if (pick_bn(m, n, true, false) == 256)
+    return launch_tc<KIND_I8, 256, 4, int32_t>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_s8_128x256");
+  return launch_tc<KIND_I8, 128, 6, int32_t>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_s8_128x128");
+}
+
+// ---- split-precision fp32 on the tensor cores ---------------------------------------------------
+// Workspace for the bf16 planes: cached, grow-only (no per-call cudaMalloc in steady state).  Calls
+// in split modes are serialised on this buffer by stream order; use one stream per library instance.
+// K extent accumulated inside the tensor core before folding into C (0 = whole K): [0] BF16X3, [1] BF16X2
+int g_split_chunk_k[2] = {512, 1024};
+struct SplitWs { void* p = nullptr; size_t bytes = 0; };
+SplitWs g_split_ws;
+
+template <int NP>
+int gemm_f32_split(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                   cudaStream_t st) {
+  const long long pka = ((long long)k + 7) & ~7LL;          // A plane pitch (elements), 16-byte multiple
+  const long long pnb = ((long long)n + 7) & ~7LL;          // B plane pitch
+  const int kp = (k + 31) & ~31;                            // B plane height: zero rows pad K to the k-block
+  const size_t a_bytes = (size_t)NP * m * pka * 2, b_bytes = (size_t)NP * kp * pnb * 2;
+  const size_t a_off = (a_bytes + 1023) & ~(size_t)1023;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_split_ws.bytes < a_off + b_bytes) {
+      if (g_split_ws.p) { cudaStreamSynchronize(st); cudaFree(g_split_ws.p); }
+      g_split_ws.p = nullptr; g_split_ws.bytes = 0;
+      cudaError_t e = cudaMalloc(&g_split_ws.p, a_off + b_bytes);
+      if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+      g_split_ws.bytes = a_off + b_bytes;
+    }
+  }
+  uint16_t* pA = reinterpret_cast<uint16_t*>(g_split_ws.p);
+  uint16_t* pB = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(g_split_ws.p) + a_off);
+  const int blocks = g_dev.sms * 8;
+  split_planes_kernel<NP><<<blocks, 256, 0, st>>>(A, lda, m, k, pA, pka, m);
+  split_planes_kernel<NP><<<blocks, 256, 0, st>>>(B, ldb, k, n, pB, pnb, kp);
+  g_launches += 2;
+  int rc = last_launch_status();
+  if (rc) return rc;
+  const int bn = pick_bn(m, n, NP == 2);
+  if constexpr (NP == 3) {
+    if (bn == 192)
+      return launch_tc<KIND_F16, 192, 3, float, ProdX3, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x3_128x192", g_split_chunk_k[0]);
+    return launch_tc<KIND_F16, 128, 4, float, ProdX3, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x3_128x128", g_split_chunk_k[0]);
+  } else {
+    if (bn == 256)
+      return launch_tc<KIND_F16, 256, 4, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x2_128x256", g_split_chunk_k[1]);
+    if (bn == 192)
+      return launch_tc<KIND_F16, 192, 5, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x2_128x192", g_split_chunk_k[1]);
+    return launch_tc<KIND_F16, 128, 6, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x2_128x128", g_split_chunk_k[1]);
+  }
 }
 
 int launch_ffma(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
@@ -215,8 +316,8 @@ int resolve_f32_mode(int mode) {
     int d = g_default_f32_mode.load();
     if (d < 0) {
       const char* e = getenv("B200GEMM_F32_MODE");
-      d = e ? atoi(e) : B200_F32_STRICT;
-      if (d < 0 || d >= B200_F32_AUTO) d = B200_F32_STRICT;
+      d = e ? atoi(e) : B200_F32_BF16X3;
+      if (d < 0 || d >= B200_F32_AUTO) d = B200_F32_BF16X3;
       g_default_f32_mode.store(d);
     }
     return d;
@@ -241,9 +342,13 @@ int gemm_f32_impl(int m, int n, int k, const float* dA, int lda, const float* dB
     case B200_F32_TF32:
       if (accumulate) return B200_ERR_UNSUPPORTED;
       if (!tma) return launch_generic<float, float>(m, n, k, dA, lda, dB, ldb, dC, ldc, 0, st, "generic_f32_64x64");
-      if (n <= 128)
-        return launch_tc<KIND_TF32, 128, 6, float>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, "tc_tf32_128x128");
-      return launch_tc<KIND_TF32, 256, 4, float>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, "tc_tf32_128x256");
+      return tc_tf32(m, n, k, dA, lda, dB, ldb, dC, ldc, st);
+    case B200_F32_BF16X3:
+      if (accumulate) return B200_ERR_UNSUPPORTED;
+      return gemm_f32_split<3>(m, n, k, dA, lda, dB, ldb, dC, ldc, st);
+    case B200_F32_BF16X2:
+      if (accumulate) return B200_ERR_UNSUPPORTED;
+      return gemm_f32_split<2>(m, n, k, dA, lda, dB, ldb, dC, ldc, st);
     default:
       return B200_ERR_UNSUPPORTED;
   }
@@ -275,6 +380,8 @@ void b200_gemm_set_default_f32_mode(int mode) {
   if (mode >= 0 && mode < B200_F32_AUTO) g_default_f32_mode.store(mode);
 }
 void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes) { g_dbg_b_lbo = lbo_bytes; g_dbg_b_sbo = sbo_bytes; }
+void b200_gemm_debug_set_bn(int bn) { g_force_bn = bn; }
+void b200_gemm_debug_set_split_chunk(int x3_k, int x2_k) { g_split_chunk_k[0] = x3_k; g_split_chunk_k[1] = x2_k; }
 
 int b200_gemm_f32(int m, int n, int k, const float* dA, int lda, const float* dB, int ldb, float* dC,
                   int ldc, int precision_mode, void* stream) {
@@ -298,12 +405,8 @@ int b200_gemm_bf16(int m, int n, int k, const uint16_t* dA, int lda, const uint1
       return launch_generic<uint16_t, float>(m, n, k, dA, lda, dB, ldb, (float*)dC, ldc, 0, st, "generic_bf16_64x64");
     return launch_generic<uint16_t, uint16_t>(m, n, k, dA, lda, dB, ldb, (uint16_t*)dC, ldc, 0, st, "generic_bf16_64x64");
   }
-  if (out_type == B200_OUT_F32) {
-    if (n <= 128) return launch_tc<KIND_F16, 128, 6, float>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, "tc_bf16_128x128");
-    return launch_tc<KIND_F16, 256, 4, float>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, "tc_bf16_128x256");
-  }
-  if (n <= 128) return launch_tc<KIND_F16, 128, 6, bf16_out>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, "tc_bf16_128x128_obf16");
-  return launch_tc<KIND_F16, 256, 4, bf16_out>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, "tc_bf16_128x256_obf16");
+  if (out_type == B200_OUT_F32) return tc_bf16_f32(m, n, k, dA, lda, dB, ldb, dC, ldc, st);
+  return tc_bf16_bf16(m, n, k, dA, lda, dB, ldb, dC, ldc, st);
 }
 
 int b200_gemm_s8s32(int m, int n, int k, const int8_t* dA, int lda, const int8_t* dB, int ldb,
@@ -317,8 +420,7 @@ int b200_gemm_s8s32(int m, int n, int k, const int8_t* dA, int lda, const int8_t
   if (k == 0) return launch_zero<int32_t>(m, n, dC, ldc, st);
   if (!tma_ok(dA, lda, dB, ldb, 1))
     return launch_generic<int8_t, int32_t>(m, n, k, dA, lda, dB, ldb, dC, ldc, 0, st, "generic_s8_64x64");
-  if (n <= 128) return launch_tc<KIND_I8, 128, 6, int32_t>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, "tc_s8_128x128");
-  return launch_tc<KIND_I8, 256, 4, int32_t>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, "tc_s8_128x256");
+  return tc_s8(m, n, k, dA, lda, dB, ldb, dC, ldc, st);
 }
 
 int b200_convert_f32_to_bf16(const float* dSrc, uint16_t* dDst, size_t count, void* stream) {

@@ -4,23 +4,29 @@
 //
 // Mapping of the reference's roles onto Blackwell:
 //   packA / packB  (aarch64/MMult_4x4_21.cpp:459-572; the gmem->smem staging of
-//                   cuda/MMult_cuda_12.cu:113-198)      -> TMA bulk-tensor copies with 128B swizzle
+//                   cuda/MMult_cuda_12.cu:113-198)      -> TMA bulk-tensor copies with hardware swizzle
 //                                                          into a STAGES-deep shared-memory ring
 //   4x4 / 8x12 register micro-kernel (kernel_8x12,
-//                   cuda/MMult_cuda_12.cu:200-206)      -> one thread issuing tcgen05.mma 128 x BN x K16
+//                   cuda/MMult_cuda_12.cu:200-206)      -> one thread issuing tcgen05.mma 128 x BN x K
 //                                                          into a TMEM accumulator (fp32 / int32)
 //   stg128 epilogue (cuda/MMult_cuda_12.cu:210-222)     -> tcgen05.ld -> swizzled smem transpose ->
 //                                                          coalesced 16-byte st.global
 //
 // Row-major B is the MMA's "MN-major" operand: no transpose pass (the job of reorder_b / trans_w in
 // aarch64-int8/MMult_4x8_21.c:45-71) exists here; TMA drops [BK x 128B] column blocks of B straight
-// into the canonical MN-major SWIZZLE_128B layout and the descriptor walks them (LBO = block stride).
+// into the canonical MN-major swizzled layout and the descriptor walks them (LBO = block stride).
+//
+// Split-precision fp32 (B200_F32_BF16X3 / _BF16X2): A and B arrive as NPA / NPB stacked bf16 "planes"
+// (a = a1 + a2 + a3, produced by split_planes_kernel); each k-block stage holds every plane once and
+// the MMA warp issues the listed plane products into the SAME fp32 accumulator, smallest terms first.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
 // warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).  Three pipelines: smem full/empty,
 // TMEM full/empty (two accumulator stages, so the epilogue of tile i overlaps the mainloop of i+1),
 // and the static persistent tile schedule.
 #pragma once
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace b200 {
@@ -34,6 +40,25 @@ template <> struct KindTraits<KIND_F16>  { static constexpr int ELEM = 2, UMMA_K
 template <> struct KindTraits<KIND_TF32> { static constexpr int ELEM = 4, UMMA_K = 8,  AB_FMT = 2, C_FMT = 1, B_LAYOUT = 1, B_SBO = 512; };
 template <> struct KindTraits<KIND_I8>   { static constexpr int ELEM = 1, UMMA_K = 32, AB_FMT = 1, C_FMT = 2, B_LAYOUT = 2, B_SBO = 1024; };
 
+// Plane products issued per k-step.  Single: plain GEMM.  X3: a=a1+a2+a3, b likewise, all terms down
+// to 2^-16 relative (a1b3, a3b1, a2b2, a1b2, a2b1, a1b1) — dropped terms are <= 2^-24.  X2: two planes,
+// three terms, dropped a2b2 ~ 2^-16.
+struct ProdSingle {
+  static constexpr int N = 1, NPA = 1, NPB = 1;
+  __host__ __device__ static constexpr int ia(int) { return 0; }
+  __host__ __device__ static constexpr int ib(int) { return 0; }
+};
+struct ProdX3 {   // (ia,ib): (0,2) (2,0) (1,1) (0,1) (1,0) (0,0)
+  static constexpr int N = 6, NPA = 3, NPB = 3;
+  __host__ __device__ static constexpr int ia(int i) { return i == 1 ? 2 : (i == 2 || i == 4) ? 1 : 0; }
+  __host__ __device__ static constexpr int ib(int i) { return i == 0 ? 2 : (i == 2 || i == 3) ? 1 : 0; }
+};
+struct ProdX2 {   // (0,1) (1,0) (0,0)
+  static constexpr int N = 3, NPA = 2, NPB = 2;
+  __host__ __device__ static constexpr int ia(int i) { return i == 1 ? 1 : 0; }
+  __host__ __device__ static constexpr int ib(int i) { return i == 0 ? 1 : 0; }
+};
+
 struct TcParams {
   void* C;
   long long ldc;           // elements
@@ -41,29 +66,39 @@ struct TcParams {
   int tiles_m, tiles_n;
   int group_m;             // rasterisation: tiles are walked m-fastest inside groups of group_m rows
   int vec_ok;              // C base and ldc allow 16-byte stores
+  int a_plane_rows;        // row offset between stacked A planes (split modes), else 0
+  int b_plane_rows;        // row offset between stacked B planes (split modes), else 0
+  int chunk_kb;            // k-blocks per accumulation chunk (two-level accumulation), >= num_kb: off
   int dbg_b_lbo, dbg_b_sbo;  // 0 = defaults (probe hook, see b200_gemm_debug_set_b_desc)
 };
 
-template <int KIND, int BN, int STAGES>
+template <int KIND, int BN, int STAGES, class Prod, int A_ROW_BYTES>
 struct TcConfig {
   using T = KindTraits<KIND>;
   static constexpr int BM = 128;
-  static constexpr int BK = 128 / T::ELEM;                 // one 128B swizzle row of K per stage
-  static constexpr int A_STAGE = BM * 128;                 // 16 KB
-  static constexpr int B_BOX_COLS = 128 / T::ELEM;         // elements per 128B-wide column block
+  static constexpr int BK = A_ROW_BYTES / T::ELEM;          // one swizzled row of K per stage
+  static constexpr int A_PLANE = BM * A_ROW_BYTES;          // 16 KB (SW128) or 8 KB (SW64)
+  static constexpr int A_LAYOUT = A_ROW_BYTES == 128 ? 2 : 4;   // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
+  static constexpr int A_SBO = 8 * A_ROW_BYTES;             // 8-row core-matrix group stride
+  static constexpr int B_BOX_COLS = 128 / T::ELEM;          // elements per 128B-wide column block
   static constexpr int B_BOXES = BN / B_BOX_COLS;
   static constexpr int B_BOX_BYTES = BK * 128;
-  static constexpr int B_STAGE = B_BOXES * B_BOX_BYTES;    // = BN * 128
+  static constexpr int B_PLANE = B_BOXES * B_BOX_BYTES;
+  static constexpr int A_STAGE = Prod::NPA * A_PLANE;
+  static constexpr int B_STAGE = Prod::NPB * B_PLANE;
   static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
-  static constexpr int MMAS_PER_STAGE = BK / T::UMMA_K;    // 4 for every kind
-  static constexpr int A_KADV = T::UMMA_K * T::ELEM;       // 32 B inside the swizzled row
-  static constexpr int B_KADV = T::UMMA_K * 128;           // UMMA_K k-rows of 128 B
-  static constexpr int EPI_STAGING = 4 * 32 * 128;         // 4 warps x 32 rows x 128 B
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int MMAS_PER_STAGE = BK / T::UMMA_K;
+  static constexpr int A_KADV = T::UMMA_K * T::ELEM;        // 32 B inside the swizzled row
+  static constexpr int B_KADV = T::UMMA_K * 128;            // UMMA_K k-rows of 128 B
+  static constexpr int EPI_STAGING = 4 * 32 * 128;          // 4 warps x 32 rows x 128 B
+  static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;  // TMEM columns between the two accumulators
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_STAGING +
                                     NUM_BARS * 8 + 16;
   static constexpr int THREADS = 192;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
+  static_assert(BN % B_BOX_COLS == 0 && BN % 16 == 0 && BN <= 256, "invalid BN");
 };
 
 __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int group_m, int& mb,
@@ -110,16 +145,16 @@ template <> struct OutPack<bf16_out> {
 template <typename OutT> struct OutBytes { static constexpr int V = 4; };
 template <> struct OutBytes<bf16_out> { static constexpr int V = 2; };
 
-template <int KIND, int BN, int STAGES, typename OutT>
+template <int KIND, int BN, int STAGES, typename OutT, class Prod, int A_ROW_BYTES>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
-  using Cfg = TcConfig<KIND, BN, STAGES>;
+  using Cfg = TcConfig<KIND, BN, STAGES, Prod, A_ROW_BYTES>;
   using T = KindTraits<KIND>;
   constexpr int OB = OutBytes<OutT>::V;
 
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1 KB
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle atoms need 1 KB
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + STAGES * Cfg::A_STAGE;
   const uint32_t sEpi = sB + STAGES * Cfg::B_STAGE;
@@ -169,11 +204,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           const uint32_t full = bar_full + 8 * s;
           mbar_arrive_expect_tx(full, Cfg::STAGE_BYTES);
-          tma_load_2d(sA + s * Cfg::A_STAGE, &tmA, full, kb * Cfg::BK, m0);
 #pragma unroll
-          for (int j = 0; j < Cfg::B_BOXES; j++)
-            tma_load_2d(sB + s * Cfg::B_STAGE + j * Cfg::B_BOX_BYTES, &tmB, full,
-                        n0 + j * Cfg::B_BOX_COLS, kb * Cfg::BK);
+          for (int pa = 0; pa < Prod::NPA; pa++)
+            tma_load_2d(sA + s * Cfg::A_STAGE + pa * Cfg::A_PLANE, &tmA, full, kb * Cfg::BK,
+                        pa * p.a_plane_rows + m0);
+#pragma unroll
+          for (int pb = 0; pb < Prod::NPB; pb++)
+#pragma unroll
+            for (int j = 0; j < Cfg::B_BOXES; j++)
+              tma_load_2d(sB + s * Cfg::B_STAGE + pb * Cfg::B_PLANE + j * Cfg::B_BOX_BYTES, &tmB, full,
+                          n0 + j * Cfg::B_BOX_COLS, pb * p.b_plane_rows + kb * Cfg::BK);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -189,25 +229,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int as = 0;
       uint32_t aph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+       for (int c0 = 0; c0 < num_kb; c0 += p.chunk_kb) {     // one TMEM accumulator per K-chunk
         mbar_wait(bar_tempty + 8 * as, aph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; kb++) {
+        const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+        const int c1 = min(c0 + p.chunk_kb, num_kb);
+        for (int kb = c0; kb < c1; kb++) {
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
           const uint32_t a0 = sA + s * Cfg::A_STAGE;
           const uint32_t b0 = sB + s * Cfg::B_STAGE;
 #pragma unroll
-          for (int k = 0; k < Cfg::MMAS_PER_STAGE; k++) {
-            const uint64_t ad = make_sdesc(a0 + k * Cfg::A_KADV, 16, 1024);
-            const uint64_t bd = make_sdesc(b0 + k * Cfg::B_KADV, b_lbo, b_sbo, T::B_LAYOUT);
-            tc_mma<KIND>(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int pr = 0; pr < Prod::N; pr++) {
+#pragma unroll
+            for (int k = 0; k < Cfg::MMAS_PER_STAGE; k++) {
+              const uint64_t ad = make_sdesc(a0 + Prod::ia(pr) * Cfg::A_PLANE + k * Cfg::A_KADV, 16,
+                                             Cfg::A_SBO, Cfg::A_LAYOUT);
+              const uint64_t bd = make_sdesc(b0 + Prod::ib(pr) * Cfg::B_PLANE + k * Cfg::B_KADV, b_lbo,
+                                             b_sbo, T::B_LAYOUT);
+              tc_mma<KIND>(d_tmem, ad, bd, idesc, ((kb - c0) | k | pr) != 0 ? 1u : 0u);
+            }
           }
           tc_commit(bar_empty + 8 * s);            // frees the smem slot when these MMAs retire
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         tc_commit(bar_tfull + 8 * as);              // accumulator complete -> epilogue
         if (++as == 2) { as = 0; aph ^= 1; }
+       }
       }
     }
   } else {
@@ -223,11 +271,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int mb, nb;
       tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, mb, nb);
       const int m0 = mb * Cfg::BM + q * 32, n0 = nb * BN;
+     // Two-level accumulation (split-precision modes): the tensor core adds into its fp32
+     // accumulator with truncation, so a long K chain drifts (measured: error grows ~K).  Each
+     // K-chunk gets a fresh TMEM accumulator and is folded into C here with a rounded fp32 add.
+     for (int c0 = 0; c0 < num_kb; c0 += p.chunk_kb) {
+      const bool fold = c0 != 0;
       mbar_wait(bar_tfull + 8 * as, aph);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::ACC_STRIDE;
 #pragma unroll 1
       for (int ps = 0; ps < PASSES; ps++) {
+        const int chunk = lane & 7;
+        const int col = n0 + ps * COLS + chunk * VEC_ELEMS;
+        const bool vec = p.vec_ok && col + VEC_ELEMS <= p.N;
+        // folding pass: fetch all eight partial-C vectors first, so their L2 latency overlaps the
+        // TMEM load and the staging transpose below
+        float4 old[8];
+        if constexpr (std::is_same<OutT, float>::value) {
+          if (fold && vec) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const int gm = m0 + i * 4 + (lane >> 3);
+              old[i] = gm < p.M ? __ldcg(reinterpret_cast<const float4*>(
+                                      reinterpret_cast<const float*>(p.C) + (long long)gm * p.ldc + col))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        }
         uint32_t ra[32], rb[32], w[32];
         tmem_ld_32x32b_x32(t_addr + ps * (COLS == 64 ? 64 : 32), ra);
         if constexpr (COLS == 64) tmem_ld_32x32b_x32(t_addr + ps * 64 + 32, rb);
@@ -246,8 +316,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
         // staging -> global: 8 lanes cover one 128-byte row segment, 4 rows per instruction
-        const int chunk = lane & 7;
-        const int col = n0 + ps * COLS + chunk * VEC_ELEMS;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
           const int row = i * 4 + (lane >> 3);
@@ -255,14 +323,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint4 v = *reinterpret_cast<const uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4));
           if (gm < p.M) {
             uint8_t* dst = reinterpret_cast<uint8_t*>(p.C) + ((long long)gm * p.ldc + col) * OB;
-            if (p.vec_ok && col + VEC_ELEMS <= p.N) {
+            if (vec) {
+              if constexpr (std::is_same<OutT, float>::value) {
+                if (fold) {
+                  v.x = __float_as_uint(__uint_as_float(v.x) + old[i].x);
+                  v.y = __float_as_uint(__uint_as_float(v.y) + old[i].y);
+                  v.z = __float_as_uint(__uint_as_float(v.z) + old[i].z);
+                  v.w = __float_as_uint(__uint_as_float(v.w) + old[i].w);
+                }
+              }
               *reinterpret_cast<uint4*>(dst) = v;
             } else {
-              const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+              uint32_t vv[4] = {v.x, v.y, v.z, v.w};
               if constexpr (OB == 4) {
 #pragma unroll
                 for (int e = 0; e < 4; e++)
-                  if (col + e < p.N) reinterpret_cast<uint32_t*>(dst)[e] = vv[e];
+                  if (col + e < p.N) {
+                    if constexpr (std::is_same<OutT, float>::value) {
+                      if (fold) vv[e] = __float_as_uint(__uint_as_float(vv[e]) + reinterpret_cast<const float*>(dst)[e]);
+                    }
+                    reinterpret_cast<uint32_t*>(dst)[e] = vv[e];
+                  }
               } else {
 #pragma unroll
                 for (int e = 0; e < 8; e++)
@@ -275,6 +356,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
       }
       if (++as == 2) { as = 0; aph ^= 1; }
+     }
     }
   }
 
@@ -283,6 +365,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---- fp32 -> stacked bf16 planes (the split-precision pre-pass) -----------------------------------
+// src: rows x cols fp32, pitch ld.  dst: NP planes stacked along rows, plane p at row p*plane_rows,
+// pitch dld (elements, multiple of 8).  x = p1 + p2 + p3 with p1 = bf16(x), p2 = bf16(x - p1),
+// p3 = bf16(x - p1 - p2); the subtractions are exact in fp32.  Rows [rows, plane_rows) and columns
+// [cols, dld) of every plane are written as zero (K padding of B must contribute nothing).
+template <int NP>
+__global__ void split_planes_kernel(const float* __restrict__ src, long long ld, int rows, int cols,
+                                    uint16_t* __restrict__ dst, long long dld, int plane_rows) {
+  const int cgroups = (int)(dld >> 2);                       // 4 columns per thread
+  const long long total = (long long)plane_rows * cgroups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cgroups);
+    const int c = (int)(i - (long long)r * cgroups) * 4;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < rows) {
+      const float* s = src + (long long)r * ld + c;
+      if (c + 4 <= cols && ((reinterpret_cast<uintptr_t>(s) & 15) == 0)) {
+        const float4 v = *reinterpret_cast<const float4*>(s);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+          if (c + e < cols) x[e] = s[e];
+      }
+    }
+#pragma unroll
+    for (int pl = 0; pl < NP; pl++) {
+      uint16_t h[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        uint32_t b;
+        asm("{\n\t.reg .b16 t;\n\tcvt.rn.bf16.f32 t, %1;\n\tmov.b32 %0, {t, t};\n\t}" : "=r"(b) : "f"(x[e]));
+        h[e] = (uint16_t)(b & 0xFFFFu);
+        x[e] -= __uint_as_float((uint32_t)h[e] << 16);
+      }
+      uint2 o = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+      *reinterpret_cast<uint2*>(dst + ((long long)pl * plane_rows + r) * dld + c) = o;
+    }
   }
 }
 

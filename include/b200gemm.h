@@ -53,10 +53,14 @@ enum b200_f32_mode {
                             arithmetic of cuda/MMult_cuda_12.cu:200-206          */
   B200_F32_TF32   = 1,   /* one tcgen05 kind::tf32 pass (10-bit mantissa inputs,
                             fp32 accumulate in TMEM)                              */
-  B200_F32_BF16X3 = 2,   /* split-bf16: a=a1+a2+a3, 6 tcgen05 kind::f16 passes,
-                            fp32-class error, tensor cores                        */
-  B200_F32_BF16X2 = 3,   /* split-bf16: a=a1+a2, 3 passes, ~2^-16 relative       */
-  B200_F32_AUTO   = 4    /* library default (see b200_gemm_default_f32_mode)      */
+  B200_F32_BF16X3 = 2,   /* split-bf16: a=a1+a2+a3, 6 tcgen05 kind::f16 products per
+                            k-step, two-level accumulation (K chunks of 512 folded
+                            into C with rounded fp32 adds): fp32-class error on the
+                            tensor cores.  THE LIBRARY DEFAULT.                    */
+  B200_F32_BF16X2 = 3,   /* split-bf16: a=a1+a2, 3 products, ~2^-17 relative       */
+  B200_F32_AUTO   = 4    /* library default: BF16X3 unless the environment variable
+                            B200GEMM_F32_MODE or b200_gemm_set_default_f32_mode
+                            says otherwise                                         */
 };
 
 /* ---- bf16 output selector -------------------------------------------------- */
@@ -119,6 +123,11 @@ int b200_convert_f32_to_bf16(const float* dSrc, uint16_t* dDst, size_t count,
  * MN-major B operand (bytes; 0 = library default).  Used only by the probe in
  * tests/ to pin the descriptor semantics on real hardware. */
 void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes);
+/* Tuning hook: force the tensor-core tile width (128, 192 or 256; 0 = built-in heuristic). */
+void b200_gemm_debug_set_bn(int bn);
+/* Tuning hook: K extent the tensor core accumulates before the epilogue folds the partial sum
+ * into C with a rounded fp32 add (two-level accumulation of the split modes); 0 = whole K. */
+void b200_gemm_debug_set_split_chunk(int bf16x3_k, int bf16x2_k);
 
 #ifdef __cplusplus
 }

@@ -176,7 +176,58 @@ def case_trunc():
     emit(case="tf32_rounding", value=float(Cg[0, 0]), truncates=bool(Cg[0, 0] == 1.0))
 
 
-CASES = {"strict": case_strict, "bf16": lambda: case_tc("bf16"), "tf32": lambda: case_tc("tf32"),
+def case_split():
+    import torch
+    o, g = _libs.load_oracle(), _libs.load_pkg()
+    for mode, name in ((g.F32_BF16X3, "bf16x3"), (g.F32_BF16X2, "bf16x2"), (g.F32_STRICT, "strict"), (g.F32_TF32, "tf32")):
+        for (m, n, k) in [(128, 192, 32), (128, 128, 64), (256, 512, 1024), (300, 520, 200), (77, 96, 80), (1000, 1100, 4096)]:
+            a, b = _libs.gen_f32(o, m, k, 5), _libs.gen_f32(o, k, n, 6)
+            t = _libs.ref_f64(o, a, b)
+            Cg = g.gemm_f32(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), mode=mode).cpu().numpy()
+            d = np.abs(Cg.astype(np.float64) - t)
+            emit(case="split_parity", mode=name, shape=[m, n, k], kernel=g.last_kernel(), maxdiff=float(d.max()),
+                 maxrel=float(d.max() / np.abs(t).max()))
+    for N in (4096, 8192):
+        A = torch.rand(N, N, device="cuda") - 0.5
+        B = torch.rand(N, N, device="cuda") - 0.5
+        Cc = torch.empty(N, N, device="cuda")
+        for mode, name in ((g.F32_BF16X3, "bf16x3"), (g.F32_BF16X2, "bf16x2"), (g.F32_TF32, "tf32")):
+            for bn in (0, 128, 192, 256):
+                g.lib.b200_gemm_debug_set_bn(bn)
+                ms = time_call(lambda: g.gemm_f32(A, B, out=Cc, mode=mode))
+                emit(case="split_time", mode=name, N=N, bn=bn, kernel=g.last_kernel(), ms=ms, tflops=2 * N ** 3 / ms / 1e9)
+        Ab, Bb = A.bfloat16(), B.bfloat16()
+        Cb = torch.empty(N, N, device="cuda", dtype=torch.bfloat16)
+        for bn in (0, 128, 192, 256):
+            g.lib.b200_gemm_debug_set_bn(bn)
+            ms = time_call(lambda: g.gemm_bf16(Ab, Bb, out=Cb))
+            emit(case="bf16_time", N=N, bn=bn, kernel=g.last_kernel(), ms=ms, tflops=2 * N ** 3 / ms / 1e9)
+        g.lib.b200_gemm_debug_set_bn(0)
+
+
+def case_chunk():
+    """Two-level accumulation: error and time of the split modes vs the K-chunk folded into C."""
+    import torch
+    o, g = _libs.load_oracle(), _libs.load_pkg()
+    m, n, k = 1000, 1100, 4096
+    a, b = _libs.gen_f32(o, m, k, 5), _libs.gen_f32(o, k, n, 6)
+    t = _libs.ref_f64(o, a, b)
+    A, B = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    N = 4096
+    A4 = torch.rand(N, N, device="cuda") - 0.5
+    B4 = torch.rand(N, N, device="cuda") - 0.5
+    C4 = torch.empty(N, N, device="cuda")
+    for mode, name in ((g.F32_BF16X3, "bf16x3"), (g.F32_BF16X2, "bf16x2")):
+        for ck in (0, 2048, 1024, 512, 256, 128):
+            g.lib.b200_gemm_debug_set_split_chunk(ck, ck)
+            Cg = g.gemm_f32(A, B, mode=mode).cpu().numpy()
+            d = np.abs(Cg.astype(np.float64) - t)
+            ms = time_call(lambda: g.gemm_f32(A4, B4, out=C4, mode=mode))
+            emit(case="chunk", mode=name, chunk_k=ck, kernel=g.last_kernel(), maxrel=float(d.max() / np.abs(t).max()),
+                 ms_4096=ms, tflops_4096=2 * N ** 3 / ms / 1e9)
+
+
+CASES = {"chunk": case_chunk, "split": case_split,"strict": case_strict, "bf16": lambda: case_tc("bf16"), "tf32": lambda: case_tc("tf32"),
          "s8": lambda: case_tc("s8"), "trunc": case_trunc}
 
 if __name__ == "__main__":

@@ -63,6 +63,43 @@ def test_f32_tf32_within_tolerance(gemm, oracle, m, n, k):
     assert np.abs(c - _libs.ref_f32_fma(oracle, a, b)).max() < 0.5
 
 
+TOL_X3 = 1e-5      # split-bf16 x3 with two-level accumulation: fp32-class (strict FFMA measures ~3e-6 at K=4096)
+TOL_X2 = 4e-5      # split-bf16 x2: dropped a2*b2 term, ~2^-17 relative
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES + [(1000, 1100, 4096), (260, 200, 1500)])
+@pytest.mark.parametrize("mode,tol", [("x3", TOL_X3), ("x2", TOL_X2)])
+def test_f32_split_bf16_modes(gemm, oracle, m, n, k, mode, tol):
+    """fp32 in / fp32 out on the tensor cores: bf16 planes (exact split of the fp32 inputs), every
+    significant cross term, K folded in chunks.  Also inside the reference harness's own 0.5 gate."""
+    md = gemm.F32_BF16X3 if mode == "x3" else gemm.F32_BF16X2
+    a, b = _libs.gen_f32(oracle, m, k, 33), _libs.gen_f32(oracle, k, n, 34)
+    c = gemm.gemm_f32(cuda(a), cuda(b), mode=md).cpu().numpy()
+    assert gemm.last_kernel().startswith("tc_bf16" + mode), gemm.last_kernel()
+    t = _libs.ref_f64(oracle, a, b)
+    assert rel(c, t) <= tol, (gemm.last_kernel(), rel(c, t))
+    assert np.abs(c - _libs.ref_f32_fma(oracle, a, b)).max() < 1e-2
+
+
+def test_f32_split_unaligned_and_default(gemm, oracle):
+    """The split pre-pass reads fp32 through plain loads, so odd leading dimensions still take the
+    tensor-core path; AUTO resolves to BF16X3 (include/b200gemm.h)."""
+    m, n, k = 200, 136, 264
+    A = cuda(_libs.gen_f32(oracle, m, k + 3, 1))[:, :k]
+    B = cuda(_libs.gen_f32(oracle, k, n + 5, 2))[:, :n]
+    Cbuf = torch.full((m, n + 7), -7.0, device="cuda")
+    assert gemm.lib.b200_gemm_default_f32_mode() == gemm.F32_BF16X3 or os.environ.get("B200GEMM_F32_MODE")
+    gemm.gemm_f32(A, B, out=Cbuf[:, :n], mode=gemm.F32_BF16X3)
+    assert gemm.last_kernel().startswith("tc_bf16x3")
+    t = _libs.ref_f64(oracle, A.cpu().numpy(), B.cpu().numpy())
+    assert rel(Cbuf[:, :n].cpu().numpy(), t) <= TOL_X3
+    assert (Cbuf[:, n:] == -7.0).all()
+    # exactly representable inputs: every mode must be exact (ones fixture of the aarch64 harness)
+    ones = torch.ones((300, 300), device="cuda")
+    for md in (gemm.F32_BF16X3, gemm.F32_BF16X2):
+        assert (gemm.gemm_f32(ones, ones, mode=md) == 300).all()
+
+
 @pytest.mark.parametrize("m,n,k", SHAPES)
 @pytest.mark.parametrize("out", ["f32", "bf16"])
 def test_bf16(gemm, oracle, m, n, k, out):
@@ -94,13 +131,13 @@ def test_s8_extremes_and_alignment(gemm, oracle):
         c = gemm.gemm_s8s32(cuda(a), cuda(b)).cpu().numpy()
         assert gemm.last_kernel().startswith("tc_s8")
         assert (c == fill_a * fill_b * k).all()
-    a, b = _libs.gen_s8(oracle, m, k + 16, 1), _libs.gen_s8(oracle, k, n + 16, 2)
+    a, b = _libs.gen_s8(oracle, m, k + 16, 1), _libs.gen_s8(oracle, k + 16, n + 16, 2)
     A, B = cuda(a), cuda(b)
-    c_tc = gemm.gemm_s8s32(A[:, :k], B[:, :n]).cpu().numpy()
+    c_tc = gemm.gemm_s8s32(A[:, :k], B[:k, :n]).cpu().numpy()
     k_tc = gemm.last_kernel()
     c_cc = gemm.gemm_s8s32(A[:, 1:k + 1], B[1:k + 1, 1:n + 1]).cpu().numpy()   # misaligned bases
     assert k_tc.startswith("tc_s8") and gemm.last_kernel().startswith("generic_s8")
-    assert np.array_equal(c_tc, _libs.ref_s8(oracle, a[:, :k], b[:, :n]))
+    assert np.array_equal(c_tc, _libs.ref_s8(oracle, a[:, :k], b[:k, :n]))
     assert np.array_equal(c_cc, _libs.ref_s8(oracle, a[:, 1:k + 1], b[1:k + 1, 1:n + 1]))
 
 
@@ -175,8 +212,11 @@ def test_full_size_properties_f32(gemm, oracle, N):
     Ct = gemm.gemm_f32(A, B, mode=gemm.F32_TF32)
     t = _libs.ref_f64(oracle, a_np, b_np)
     assert rel(Ct[rows].cpu().numpy(), t) <= TOL_TF32
-    # (3) whole-matrix agreement of the two independent GPU paths (catches tile-scheduling holes)
+    Cx = gemm.gemm_f32(A, B, mode=gemm.F32_BF16X3)
+    assert rel(Cx[rows].cpu().numpy(), t) <= TOL_X3
+    # (3) whole-matrix agreement of the independent GPU paths (catches tile-scheduling holes)
     assert float((Cs - Ct).abs().max() / Cs.abs().max()) <= TOL_TF32
+    assert float((Cs - Cx).abs().max() / Cs.abs().max()) <= 2 * TOL_X3
     # (4) linearity in A, exact for power-of-two scaling
     assert torch.equal(gemm.gemm_f32(A * 2, B, mode=gemm.F32_TF32), Ct * 2)
     # (5) checksum of checksums: sum_j C(i,j) == A(i,:) . rowsum(B)   (fp64 on device)
