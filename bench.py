@@ -209,29 +209,19 @@ def main():
         A = torch.rand((Mloc, K), device=dev, generator=gen) * 2 - 1
         B = torch.rand((K, N), device=dev, generator=gen) * 2 - 1 if (rank == 0 or world == 1) else torch.empty((K, N), device=dev)
         Cm = torch.empty((Mloc, N), device=dev)
-        Bp = torch.empty((npan, K, PANEL), device=dev) if world > 1 else None     # panel staging / receive buffers
-        sets.append((A, B, Cm, Bp))
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+        sets.append((A, B, Cm, None))
+    rp = None
+    if world > 1:
+        rowpanel = __import__("importlib").import_module(_libs.PKG + ".rowpanel")
+        rp = rowpanel.RowPanelGemm(lambda a, b, out: g.gemm_f32(a, b, out=out, mode=mode), dist, rank, world,
+                                   K, N, PANEL, dev, torch.float32)
 
     def step(i):
-        A, B, Cm, Bp = sets[i % R]
+        A, B, Cm, _ = sets[i % R]
         if world == 1:
             g.gemm_f32(A, B, out=Cm, mode=mode)
-            return
-        cur = torch.cuda.current_stream()
-        comm.wait_stream(cur)
-        evs = []
-        with torch.cuda.stream(comm):
-            for j in range(npan):
-                if rank == 0:
-                    Bp[j].copy_(B[:, j * PANEL:(j + 1) * PANEL])          # pack the column panel (inside the timed region)
-                dist.broadcast(Bp[j], src=0)
-                e = torch.cuda.Event()
-                e.record(comm)
-                evs.append(e)
-        for j in range(npan):
-            cur.wait_event(evs[j])
-            g.gemm_f32(A, Bp[j], out=Cm[:, j * PANEL:(j + 1) * PANEL], mode=mode)   # GEMM on panel j while j+1.. are in flight
+        else:
+            rp.run(A, B, Cm)        # pack + NCCL broadcast of B by column panel, GEMM per panel as it lands
 
     def barrier():
         if world > 1:
@@ -245,6 +235,7 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = g.launch_count()
+    g.lib.b200_gemm_debug_kernel_timing(1)      # event pair around every dominant-kernel launch, same stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -253,6 +244,8 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = g.launch_count() - l0
+    kern_ms_sum, kern_launches = g.kernel_time_ms()
+    g.lib.b200_gemm_debug_kernel_timing(0)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms_total], device=dev)
@@ -306,11 +299,17 @@ def main():
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
         "published_reference": {"MMult_cuda_12 @4096 on RTX 3090": 21410.87, "note": "other hardware; BASELINE.json.published is {}"},
     }
-    # roofline of the dominant kernel: one GEMM launch per step (N=1) -> kernel time == step time
+    # roofline of the dominant kernel: its own launch durations (CUDA events on the launching stream,
+    # recorded inside the timed region); algorithmic flops = 2*M*N*K, no credit for the 6 split passes
     if world == 1:
-        achieved = 2.0 * N0 ** 3 / (ms * 1e-3) / 1e12
+        kern_ms = kern_ms_sum / max(kern_launches, 1)
+        achieved = 2.0 * N0 ** 3 / (kern_ms * 1e-3) / 1e12
         out["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                            "frac": achieved / pk["bf16_tflops"], "traffic": None,
+                           "kernel_ms": kern_ms, "kernel_launches_timed": kern_launches,
+                           "kernel_share_of_step": kern_ms / ms,
+                           "tensor_pipe_flops_per_launch": 2.0 * N0 ** 3 * {2: 6, 3: 3}.get(mode, 1),
+                           "tensor_pipe_frac": achieved * {2: 6, 3: 3}.get(mode, 1) / ({1: 0.5}.get(mode, 1.0) * pk["bf16_tflops"]),
                            "peak_source": pk["source"] + ", burst bf16; sustained " + str(pk["bf16_tflops_sustained"]),
                            "frac_of_sustained": achieved / pk["bf16_tflops_sustained"] if pk["bf16_tflops_sustained"] else None,
                            "algorithmic_flops_per_launch": 2.0 * N0 ** 3,

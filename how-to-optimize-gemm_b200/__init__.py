@@ -24,7 +24,7 @@ EXPORTS = [
     "b200_gemm_launch_count", "b200_gemm_default_f32_mode", "b200_gemm_set_default_f32_mode",
     "b200_gemm_f32", "b200_gemm_f32_host", "b200_gemm_bf16", "b200_gemm_s8s32",
     "b200_gemm_s8s32_host", "b200_convert_f32_to_bf16", "b200_gemm_debug_set_b_desc", "b200_gemm_debug_set_bn",
-    "b200_gemm_debug_set_split_chunk",
+    "b200_gemm_debug_set_split_chunk", "b200_gemm_debug_kernel_timing", "b200_gemm_debug_kernel_time_ms",
 ]
 
 
@@ -56,6 +56,15 @@ lib.b200_gemm_debug_set_b_desc.argtypes = [_i, _i]
 lib.b200_gemm_set_default_f32_mode.argtypes = [_i]
 lib.b200_gemm_debug_set_bn.argtypes = [_i]
 lib.b200_gemm_debug_set_split_chunk.argtypes = [_i, _i]
+lib.b200_gemm_debug_kernel_timing.argtypes = [_i]
+lib.b200_gemm_debug_kernel_time_ms.argtypes = [C.POINTER(C.c_double)]
+
+
+def kernel_time_ms():
+    """(sum_ms, launches) of the dominant GEMM kernel since kernel timing was enabled."""
+    s = C.c_double(0.0)
+    n = lib.b200_gemm_debug_kernel_time_ms(C.byref(s))
+    return s.value, n
 
 
 def _check(rc):

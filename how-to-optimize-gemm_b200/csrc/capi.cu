@@ -25,6 +25,25 @@ using namespace b200;
 namespace {
 
 std::atomic<unsigned long long> g_launches{0};
+
+// Optional per-launch timing of the dominant GEMM kernel (bench.py's roofline.achieved): a pair of
+// CUDA events is recorded on the launching stream around the kernel.  Off by default.
+struct KernelTimer {
+  static constexpr int CAP = 1024;
+  bool on = false;
+  int n = 0;
+  cudaEvent_t ev[CAP][2] = {};
+  void begin(cudaStream_t st) {
+    if (!on || n >= CAP) return;
+    if (!ev[n][0]) { cudaEventCreate(&ev[n][0]); cudaEventCreate(&ev[n][1]); }
+    cudaEventRecord(ev[n][0], st);
+  }
+  void end(cudaStream_t st) {
+    if (!on || n >= CAP) return;
+    cudaEventRecord(ev[n][1], st);
+    n++;
+  }
+} g_ktimer;
 std::atomic<int> g_default_f32_mode{-1};
 thread_local const char* t_last_kernel = "none";
 int g_dbg_b_lbo = 0, g_dbg_b_sbo = 0;
@@ -183,7 +202,9 @@ int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_tota
   }
   int tiles = p.tiles_m * p.tiles_n;
   int grid = tiles < g_dev.sms ? tiles : g_dev.sms;
+  g_ktimer.begin(st);
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  g_ktimer.end(st);
   g_launches++;
   t_last_kernel = name;
   return last_launch_status();
@@ -301,7 +322,9 @@ int launch_ffma(int m, int n, int k, const float* A, int lda, const float* B, in
     attr_set = true;
   }
   dim3 grid((n + Cfg::BN - 1) / Cfg::BN, (m + Cfg::BM - 1) / Cfg::BM);
+  g_ktimer.begin(st);
   gemm_ffma_kernel<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  g_ktimer.end(st);
   g_launches++;
   t_last_kernel = "ffma_128x128x32_tma";
   return last_launch_status();
@@ -382,6 +405,20 @@ void b200_gemm_set_default_f32_mode(int mode) {
 void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes) { g_dbg_b_lbo = lbo_bytes; g_dbg_b_sbo = sbo_bytes; }
 void b200_gemm_debug_set_bn(int bn) { g_force_bn = bn; }
 void b200_gemm_debug_set_split_chunk(int x3_k, int x2_k) { g_split_chunk_k[0] = x3_k; g_split_chunk_k[1] = x2_k; }
+void b200_gemm_debug_kernel_timing(int enable) { g_ktimer.on = enable != 0; g_ktimer.n = 0; }
+int b200_gemm_debug_kernel_time_ms(double* sum_ms) {
+  double sum = 0;
+  int cnt = 0;
+  for (int i = 0; i < g_ktimer.n; i++) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(g_ktimer.ev[i][1]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, g_ktimer.ev[i][0], g_ktimer.ev[i][1]) == cudaSuccess) { sum += ms; cnt++; }
+  }
+  cudaGetLastError();
+  g_ktimer.n = 0;
+  if (sum_ms) *sum_ms = sum;
+  return cnt;
+}
 
 int b200_gemm_f32(int m, int n, int k, const float* dA, int lda, const float* dB, int ldb, float* dC,
                   int ldc, int precision_mode, void* stream) {

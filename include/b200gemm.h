@@ -128,6 +128,12 @@ void b200_gemm_debug_set_bn(int bn);
 /* Tuning hook: K extent the tensor core accumulates before the epilogue folds the partial sum
  * into C with a rounded fp32 add (two-level accumulation of the split modes); 0 = whole K. */
 void b200_gemm_debug_set_split_chunk(int bf16x3_k, int bf16x2_k);
+/* Measurement hook: while enabled, a CUDA-event pair is recorded on the launching stream around
+ * every dominant GEMM kernel launch (not the split pre-pass).  b200_gemm_debug_kernel_time_ms
+ * synchronises those events, stores the summed kernel time and returns the number of launches
+ * covered (then resets).  bench.py's roofline.achieved comes from here. */
+void b200_gemm_debug_kernel_timing(int enable);
+int  b200_gemm_debug_kernel_time_ms(double* sum_ms);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,73 @@
+"""The N>1 path on CPU: world_size-2 `gloo` run of the row-panel shard + column-panel broadcast of B
+(how-to-optimize-gemm_b200/rowpanel.py).  The local kernel is a host stand-in (the oracle's
+REF_MMult arithmetic) — this checks partitioning and the exchange step, not the CUDA kernels."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import _libs
+
+torch = pytest.importorskip("torch")
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, M, N, K, panel, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import importlib
+    import _libs as L
+    sys.path.insert(0, L.ROOT)
+    rowpanel = importlib.import_module(L.PKG + ".rowpanel")   # pure-python module: does not need the GPU library
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    o = L.load_oracle()
+    o.oracle_set_threads(1)
+
+    def host_gemm(a, b, out):
+        c = L.ref_f32_fma(o, np.ascontiguousarray(a.numpy()), np.ascontiguousarray(b.numpy()))
+        out.copy_(torch.from_numpy(c))
+
+    A = torch.from_numpy(L.gen_f32(o, M, K, 100))
+    B = torch.from_numpy(L.gen_f32(o, K, N, 200)) if rank == 0 else None
+    r0, r1 = rowpanel.row_panel(rank, world, M)
+    rp = rowpanel.RowPanelGemm(host_gemm, dist, rank, world, K, N, panel, torch.device("cpu"), torch.float32)
+    C = torch.full((r1 - r0, N), float("nan"))
+    rp.run(A[r0:r1], B, C)
+    np.save(os.path.join(out_dir, f"c_{rank}.npy"), C.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("M,N,K,panel", [(37, 50, 29, 16), (64, 96, 40, 32)])
+def test_rowpanel_world2(tmp_path, oracle, M, N, K, panel):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), M, N, K, panel, str(tmp_path)), nprocs=world, join=True)
+    C = np.concatenate([np.load(tmp_path / f"c_{r}.npy") for r in range(world)], axis=0)
+    a, b = _libs.gen_f32(oracle, M, K, 100), _libs.gen_f32(oracle, K, N, 200)
+    assert np.array_equal(C, _libs.ref_f32_fma(oracle, a, b))
+
+
+def test_partition_helpers():
+    import importlib
+    sys.path.insert(0, _libs.ROOT)
+    rowpanel = importlib.import_module(_libs.PKG + ".rowpanel")
+    for M in (1, 7, 16384, 4097):
+        for world in (1, 2, 3, 4, 8):
+            spans = [rowpanel.row_panel(r, world, M) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == M
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert rowpanel.column_panels(4096, 1024) == [(0, 1024), (1024, 2048), (2048, 3072), (3072, 4096)]
+    assert rowpanel.column_panels(100, 48) == [(0, 48), (48, 96), (96, 100)]
