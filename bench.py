@@ -319,7 +319,9 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                out["roofline"]["traffic"] = json.load(open(tp)).get(kernel_name)
+                # bytes per launch (dram read+write) of this kernel at this size from the committed
+                # `ncu --set full` capture (profiles/, tools/summarize_ncu.py); null if not captured
+                out["roofline"]["traffic"] = json.load(open(tp)).get(f"{kernel_name}@{N0}")
             except Exception:
                 pass
 

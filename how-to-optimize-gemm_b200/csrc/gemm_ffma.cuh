@@ -73,18 +73,25 @@ gemm_ffma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int kb = 0; kb < Cfg::STAGES - 1 && kb < num_kb; kb++) issue(kb);
   }
 
-  float acc[8][8];
+  // Accumulators as 64-bit pairs: Blackwell's packed FFMA2 (fma.rn.f32x2) performs two fused
+  // multiply-adds per lane per instruction; ptxas folds the scalar A operand into the instruction's
+  // broadcast form (FFMA2 Rd, Ra.F32, Rb.F32x2, Rc.F32x2), so one k-step is 32 FFMA2 instead of 64
+  // FFMA — half the issue slots and register-port reads, same rounding (each lane is an IEEE fma).
+  float2 acc[8][4];
 #pragma unroll
   for (int i = 0; i < 8; i++)
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[i][j] = 0.0f;
+    for (int j = 0; j < 4; j++) acc[i][j] = make_float2(0.0f, 0.0f);
   if (p.accumulate) {
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         const int gm = m0 + ty + 16 * i, gn = n0 + tx * 4 + 64 * (j >> 2) + (j & 3);
-        if (gm < p.M && gn < p.N) acc[i][j] = p.C[(long long)gm * p.ldc + gn];
+        if (gm < p.M && gn < p.N) {
+          const float v = p.C[(long long)gm * p.ldc + gn];
+          if (j & 1) acc[i][j >> 1].y = v; else acc[i][j >> 1].x = v;
+        }
       }
   }
 
@@ -118,12 +125,14 @@ gemm_ffma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint8_t* brow = Bs + (kc * 4 + kk) * 512 + b_col_off;
         const float4 b0 = *reinterpret_cast<const float4*>(brow);
         const float4 b1 = *reinterpret_cast<const float4*>(brow + 256);
-        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const float2 bv[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w),
+                              make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
         for (int i = 0; i < 8; i++) {
           const float av = kk == 0 ? a4[i].x : kk == 1 ? a4[i].y : kk == 2 ? a4[i].z : a4[i].w;
+          const float2 aa = make_float2(av, av);
 #pragma unroll
-          for (int j = 0; j < 8; j++) acc[i][j] = fmaf(av, bv[j], acc[i][j]);
+          for (int j = 0; j < 4; j++) acc[i][j] = __ffma2_rn(aa, bv[j], acc[i][j]);
         }
       }
     }
@@ -142,11 +151,12 @@ gemm_ffma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float* dst = p.C + (long long)gm * p.ldc + gn;
       if (p.vec_ok && gn + 4 <= p.N) {
         *reinterpret_cast<float4*>(dst) =
-            make_float4(acc[i][4 * j], acc[i][4 * j + 1], acc[i][4 * j + 2], acc[i][4 * j + 3]);
+            make_float4(acc[i][2 * j].x, acc[i][2 * j].y, acc[i][2 * j + 1].x, acc[i][2 * j + 1].y);
       } else {
+        const float ev[4] = {acc[i][2 * j].x, acc[i][2 * j].y, acc[i][2 * j + 1].x, acc[i][2 * j + 1].y};
 #pragma unroll
         for (int e = 0; e < 4; e++)
-          if (gn + e < p.N) dst[e] = acc[i][4 * j + e];
+          if (gn + e < p.N) dst[e] = ev[e];
       }
     }
   }
