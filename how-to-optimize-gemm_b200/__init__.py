@@ -25,6 +25,7 @@ EXPORTS = [
     "b200_gemm_f32", "b200_gemm_f32_host", "b200_gemm_bf16", "b200_gemm_s8s32",
     "b200_gemm_s8s32_host", "b200_convert_f32_to_bf16", "b200_gemm_debug_set_b_desc", "b200_gemm_debug_set_bn",
     "b200_gemm_debug_set_split_chunk", "b200_gemm_debug_kernel_timing", "b200_gemm_debug_kernel_time_ms",
+    "b200_gemm_debug_set_cta_group", "b200_gemm_debug_set_split_tail",
 ]
 
 
@@ -57,6 +58,8 @@ lib.b200_gemm_set_default_f32_mode.argtypes = [_i]
 lib.b200_gemm_debug_set_bn.argtypes = [_i]
 lib.b200_gemm_debug_set_split_chunk.argtypes = [_i, _i]
 lib.b200_gemm_debug_kernel_timing.argtypes = [_i]
+lib.b200_gemm_debug_set_cta_group.argtypes = [_i]
+lib.b200_gemm_debug_set_split_tail.argtypes = [_i]
 lib.b200_gemm_debug_kernel_time_ms.argtypes = [C.POINTER(C.c_double)]
 
 

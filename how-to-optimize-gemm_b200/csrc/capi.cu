@@ -25,6 +25,9 @@ using namespace b200;
 namespace {
 
 std::atomic<unsigned long long> g_launches{0};
+int g_split_tail = 1;        // test/tuning hook (b200_gemm_debug_set_split_tail): 0 = whole tiles only
+int* g_flags = nullptr;      // tail-split ordering flags (zero between launches), 16 rotating slots of 1024 ints
+unsigned g_flag_slot = 0;
 
 // Optional per-launch timing of the dominant GEMM kernel (bench.py's roofline.achieved): a pair of
 // CUDA events is recorded on the launching stream around the kernel.  Off by default.
@@ -80,6 +83,11 @@ int ensure_device() {
       return B200_ERR_NO_DEVICE;
     }
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  if (!g_flags) {
+    if (cudaMalloc(&g_flags, 16 * 1024 * sizeof(int)) != cudaSuccess || cudaMemset(g_flags, 0, 16 * 1024 * sizeof(int)) != cudaSuccess) {
+      cudaGetLastError(); g_flags = nullptr; g_dev.ok = -1; return B200_ERR_NO_DEVICE;
+    }
   }
   g_dev.ok = 1;
   g_dev.dev = dev;
@@ -164,13 +172,14 @@ int launch_generic(int m, int n, int k, const InT* A, int lda, const InT* B, int
 }
 
 // ---- tensor-core launch -------------------------------------------------------------------
-int g_force_bn = 0;          // test/tuning hook (B200GEMM_BN or b200_gemm_debug_set_bn): 0 = heuristic
+int g_force_bn = 0;          // test/tuning hook (b200_gemm_debug_set_bn): 0 = heuristic
+int g_force_cg = 0;          // test/tuning hook (b200_gemm_debug_set_cta_group): 0 = auto, 1, 2
 
-template <int KIND, int BN, int STAGES, typename OutT, class Prod = ProdSingle, int A_ROW_BYTES = 128>
+template <int KIND, int BN, int STAGES, typename OutT, class Prod = ProdSingle, int A_ROW_BYTES = 128, int CG = 1>
 int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_total, int a_plane_rows,
               const void* B, long long ldb, int b_rows_total, int b_plane_rows, void* C, int ldc,
               cudaStream_t st, const char* name, int chunk_k = 0) {
-  using Cfg = TcConfig<KIND, BN, STAGES, Prod, A_ROW_BYTES>;
+  using Cfg = TcConfig<KIND, BN, STAGES, Prod, A_ROW_BYTES, CG>;
   using T = KindTraits<KIND>;
   constexpr CUtensorMapDataType dt = KIND == KIND_F16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                    : KIND == KIND_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
@@ -184,16 +193,16 @@ int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_tota
   if (rc) return rc;
   TcParams p;
   p.C = C; p.ldc = ldc; p.M = m; p.N = n; p.K = k;
-  p.tiles_m = (m + Cfg::BM - 1) / Cfg::BM;
+  p.tiles_m = (m + Cfg::TILE_M - 1) / Cfg::TILE_M;
   p.tiles_n = (n + BN - 1) / BN;
-  p.group_m = 16;
+  p.group_m = 16 / CG;     // 2048 rows of A per raster group either way
   constexpr int OB = OutBytes<OutT>::V;
   p.vec_ok = aligned16(C) && ((long long)ldc * OB) % 16 == 0;
   p.a_plane_rows = a_plane_rows; p.b_plane_rows = b_plane_rows;
   p.chunk_kb = chunk_k > 0 ? (chunk_k + Cfg::BK - 1) / Cfg::BK : (k + Cfg::BK - 1) / Cfg::BK;
   if (p.chunk_kb < 1) p.chunk_kb = 1;
   p.dbg_b_lbo = g_dbg_b_lbo; p.dbg_b_sbo = g_dbg_b_sbo;
-  auto kern = gemm_tc_kernel<KIND, BN, STAGES, OutT, Prod, A_ROW_BYTES>;
+  auto kern = gemm_tc_kernel<KIND, BN, STAGES, OutT, Prod, A_ROW_BYTES, CG>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -201,9 +210,40 @@ int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_tota
     attr_set = true;
   }
   int tiles = p.tiles_m * p.tiles_n;
-  int grid = tiles < g_dev.sms ? tiles : g_dev.sms;
+  const int units_max = g_dev.sms / CG;                 // CTAs, or CTA pairs (one per TPC)
+  // Wave quantisation: the last, partial round of tiles (or the only round of a small problem) is
+  // cut along K so that every CTA/pair has work: rem tiles x split parts <= units.
+  const int num_kb = (k + Cfg::BK - 1) / Cfg::BK;
+  const int rem = tiles % units_max;
+  int split = 1;
+  if (g_split_tail && OB == 4 && rem > 0) {
+    split = units_max / rem;
+    if (split > 4) split = 4;
+    if (split > num_kb / 8) split = num_kb / 8;       // keep >= 8 k-blocks per part
+    if (split < 1) split = 1;
+    if (rem * CG * 4 > 1024) split = 1;               // flag slot capacity
+  }
+  p.split = split;
+  p.full_tiles = split > 1 ? tiles - rem : tiles;
+  p.flags = g_flags + (g_flag_slot++ % 16) * 1024;
+  const int items = p.full_tiles + (tiles - p.full_tiles) * split;
+  const int units = items < units_max ? items : units_max;
   g_ktimer.begin(st);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  if constexpr (CG == 1) {
+    kern<<<units, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(units * CG);
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+  }
   g_ktimer.end(st);
   g_launches++;
   t_last_kernel = name;
@@ -232,7 +272,18 @@ int pick_bn(int m, int n, bool allow256, bool allow192 = true) {
   return best;
 }
 
+// CTA pairs (tcgen05 cta_group::2, 256 x BN per pair): each CTA stages only its half of B, halving the
+// shared-memory operand traffic per MMA that bounds the 1-CTA kernel.  Used whenever C has at least
+// two 128-row blocks.
+bool use_pair(int m, int n) {
+  if (g_force_cg == 1) return false;
+  if (g_force_cg == 2) return true;
+  return m > 128 && n > 128;
+}
+
 #define TC_PLAIN(KIND, OUT, NAME)                                                                     \
+  if (use_pair(m, n))                                                                                 \
+    return launch_tc<KIND, 256, 6, OUT, ProdSingle, 128, 2>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, NAME "_2cta_256x256"); \
   switch (pick_bn(m, n, true)) {                                                                      \
     case 256: return launch_tc<KIND, 256, 4, OUT>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, NAME "_128x256"); \
     case 192: return launch_tc<KIND, 192, 5, OUT>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, NAME "_128x192"); \
@@ -250,6 +301,8 @@ int tc_bf16_bf16(int m, int n, int k, const void* A, int lda, const void* B, int
 }
 int tc_s8(int m, int n, int k, const void* A, int lda, const void* B, int ldb, void* C, int ldc, cudaStream_t st) {
   // int8 column blocks are 128 elements wide (128 B): BN = 192 is not a whole number of them
+  if (use_pair(m, n))
+    return launch_tc<KIND_I8, 256, 6, int32_t, ProdSingle, 128, 2>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_s8_2cta_256x256");
   if (pick_bn(m, n, true, false) == 256)
     return launch_tc<KIND_I8, 256, 4, int32_t>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_s8_128x256");
   return launch_tc<KIND_I8, 128, 6, int32_t>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_s8_128x128");
@@ -289,6 +342,12 @@ int gemm_f32_split(int m, int n, int k, const float* A, int lda, const float* B,
   g_launches += 2;
   int rc = last_launch_status();
   if (rc) return rc;
+  if (use_pair(m, n)) {
+    if constexpr (NP == 3)
+      return launch_tc<KIND_F16, 256, 4, float, ProdX3, 64, 2>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x3_2cta_256x256", g_split_chunk_k[0]);
+    else
+      return launch_tc<KIND_F16, 256, 6, float, ProdX2, 64, 2>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x2_2cta_256x256", g_split_chunk_k[1]);
+  }
   const int bn = pick_bn(m, n, NP == 2);
   if constexpr (NP == 3) {
     if (bn == 192)
@@ -404,6 +463,8 @@ void b200_gemm_set_default_f32_mode(int mode) {
 }
 void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes) { g_dbg_b_lbo = lbo_bytes; g_dbg_b_sbo = sbo_bytes; }
 void b200_gemm_debug_set_bn(int bn) { g_force_bn = bn; }
+void b200_gemm_debug_set_cta_group(int cg) { g_force_cg = cg; }
+void b200_gemm_debug_set_split_tail(int on) { g_split_tail = on; }
 void b200_gemm_debug_set_split_chunk(int x3_k, int x2_k) { g_split_chunk_k[0] = x3_k; g_split_chunk_k[1] = x2_k; }
 void b200_gemm_debug_kernel_timing(int enable) { g_ktimer.on = enable != 0; g_ktimer.n = 0; }
 int b200_gemm_debug_kernel_time_ms(double* sum_ms) {

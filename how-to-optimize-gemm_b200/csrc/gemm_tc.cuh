@@ -69,10 +69,15 @@ struct TcParams {
   int a_plane_rows;        // row offset between stacked A planes (split modes), else 0
   int b_plane_rows;        // row offset between stacked B planes (split modes), else 0
   int chunk_kb;            // k-blocks per accumulation chunk (two-level accumulation), >= num_kb: off
+  // Wave-quantisation tail: work items [0, full_tiles) are whole tiles; every later tile is cut
+  // into `split` K-ranges processed by different CTAs/pairs in the last round and folded into C in
+  // order (part p waits for flag == p on its 32-row strip, adds, then publishes p+1).
+  int full_tiles, split;
+  int* flags;              // [tail tile][cta rank][epilogue warp], zero between launches
   int dbg_b_lbo, dbg_b_sbo;  // 0 = defaults (probe hook, see b200_gemm_debug_set_b_desc)
 };
 
-template <int KIND, int BN, int STAGES, class Prod, int A_ROW_BYTES>
+template <int KIND, int BN, int STAGES, class Prod, int A_ROW_BYTES, int CG = 1>
 struct TcConfig {
   using T = KindTraits<KIND>;
   static constexpr int BM = 128;
@@ -81,12 +86,14 @@ struct TcConfig {
   static constexpr int A_LAYOUT = A_ROW_BYTES == 128 ? 2 : 4;   // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
   static constexpr int A_SBO = 8 * A_ROW_BYTES;             // 8-row core-matrix group stride
   static constexpr int B_BOX_COLS = 128 / T::ELEM;          // elements per 128B-wide column block
-  static constexpr int B_BOXES = BN / B_BOX_COLS;
+  static constexpr int BN_CTA = BN / CG;                    // B columns held by each CTA of the pair
+  static constexpr int B_BOXES = BN_CTA / B_BOX_COLS;
   static constexpr int B_BOX_BYTES = BK * 128;
   static constexpr int B_PLANE = B_BOXES * B_BOX_BYTES;
   static constexpr int A_STAGE = Prod::NPA * A_PLANE;
   static constexpr int B_STAGE = Prod::NPB * B_PLANE;
-  static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
+  static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;     // per CTA
+  static constexpr int TX_BYTES = CG * STAGE_BYTES;         // bytes landing on the (leader's) full barrier
   static constexpr int MMAS_PER_STAGE = BK / T::UMMA_K;
   static constexpr int A_KADV = T::UMMA_K * T::ELEM;        // 32 B inside the swizzled row
   static constexpr int B_KADV = T::UMMA_K * 128;            // UMMA_K k-rows of 128 B
@@ -98,7 +105,8 @@ struct TcConfig {
                                     NUM_BARS * 8 + 16;
   static constexpr int THREADS = 192;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
-  static_assert(BN % B_BOX_COLS == 0 && BN % 16 == 0 && BN <= 256, "invalid BN");
+  static_assert(BN_CTA % B_BOX_COLS == 0 && BN % 16 == 0 && BN <= 256, "invalid BN");
+  static constexpr int TILE_M = 128 * CG;                   // rows of C per work unit (CTA or CTA pair)
 };
 
 __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int group_m, int& mb,
@@ -110,6 +118,18 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
   const int r = t - g * per_group;
   mb = first_m + r % rows;
   nb = r / rows;
+}
+
+struct WorkItem { int tile, part, kb0, kb1; };
+__device__ __forceinline__ WorkItem work_item(int w, const TcParams& p, int num_kb) {
+  WorkItem it;
+  if (w < p.full_tiles) { it.tile = w; it.part = 0; it.kb0 = 0; it.kb1 = num_kb; return it; }
+  const int r = w - p.full_tiles;
+  it.tile = p.full_tiles + r / p.split;
+  it.part = r - (r / p.split) * p.split;
+  it.kb0 = (int)((long long)num_kb * it.part / p.split);
+  it.kb1 = (int)((long long)num_kb * (it.part + 1) / p.split);
+  return it;
 }
 
 template <typename OutT> struct OutPack;
@@ -145,11 +165,11 @@ template <> struct OutPack<bf16_out> {
 template <typename OutT> struct OutBytes { static constexpr int V = 4; };
 template <> struct OutBytes<bf16_out> { static constexpr int V = 2; };
 
-template <int KIND, int BN, int STAGES, typename OutT, class Prod, int A_ROW_BYTES>
+template <int KIND, int BN, int STAGES, typename OutT, class Prod, int A_ROW_BYTES, int CG>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
-  using Cfg = TcConfig<KIND, BN, STAGES, Prod, A_ROW_BYTES>;
+  using Cfg = TcConfig<KIND, BN, STAGES, Prod, A_ROW_BYTES, CG>;
   using T = KindTraits<KIND>;
   constexpr int OB = OutBytes<OutT>::V;
 
@@ -168,6 +188,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CTA pair (CG == 2): rank 0 is the leader — it owns the full[] and tmem_empty[] barriers the whole
+  // pair signals, and its MMA thread issues tcgen05.mma.cta_group::2 for both SMs.
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -178,17 +204,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 4);
+      mbar_init(bar_tempty + 8 * i, 4 * CG);     // one arrive per epilogue warp of every CTA in the pair
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(s_tmem_ptr);
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_cg2<Cfg::TMEM_COLS>(s_tmem_ptr);
+    else tmem_alloc<Cfg::TMEM_COLS>(s_tmem_ptr);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync(); else __syncthreads();   // peers touch each other's barriers
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (s_tmem_ptr - smem_base));
 
   const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_items = p.full_tiles + (num_tiles - p.full_tiles) * p.split;
   const int num_kb = (p.K + Cfg::BK - 1) / Cfg::BK;
 
   if (warp == 0) {
@@ -196,44 +226,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int w = unit; w < num_items; w += num_units) {
+        const WorkItem it = work_item(w, p, num_kb);
         int mb, nb;
-        tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, mb, nb);
-        const int m0 = mb * Cfg::BM, n0 = nb * BN;
-        for (int kb = 0; kb < num_kb; kb++) {
+        tile_coords(it.tile, p.tiles_m, p.tiles_n, p.group_m, mb, nb);
+        // this CTA's slice of the unit: its 128 rows of A, its BN/CG columns of B
+        const int m0 = mb * Cfg::TILE_M + (int)cta_rank * Cfg::BM, n0 = nb * BN + (int)cta_rank * Cfg::BN_CTA;
+        for (int kb = it.kb0; kb < it.kb1; kb++) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          const uint32_t full = bar_full + 8 * s;
-          mbar_arrive_expect_tx(full, Cfg::STAGE_BYTES);
+          // bytes from both CTAs complete on the LEADER's full barrier; only the leader arms it
+          const uint32_t full = CG == 2 ? mapa(bar_full + 8 * s, 0) : bar_full + 8 * s;
+          if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::TX_BYTES);
 #pragma unroll
-          for (int pa = 0; pa < Prod::NPA; pa++)
-            tma_load_2d(sA + s * Cfg::A_STAGE + pa * Cfg::A_PLANE, &tmA, full, kb * Cfg::BK,
-                        pa * p.a_plane_rows + m0);
+          for (int pa = 0; pa < Prod::NPA; pa++) {
+            const uint32_t dst = sA + s * Cfg::A_STAGE + pa * Cfg::A_PLANE;
+            if constexpr (CG == 2) tma_load_2d_cg2(dst, &tmA, full, kb * Cfg::BK, pa * p.a_plane_rows + m0);
+            else tma_load_2d(dst, &tmA, full, kb * Cfg::BK, pa * p.a_plane_rows + m0);
+          }
 #pragma unroll
           for (int pb = 0; pb < Prod::NPB; pb++)
 #pragma unroll
-            for (int j = 0; j < Cfg::B_BOXES; j++)
-              tma_load_2d(sB + s * Cfg::B_STAGE + pb * Cfg::B_PLANE + j * Cfg::B_BOX_BYTES, &tmB, full,
-                          n0 + j * Cfg::B_BOX_COLS, pb * p.b_plane_rows + kb * Cfg::BK);
+            for (int j = 0; j < Cfg::B_BOXES; j++) {
+              const uint32_t dst = sB + s * Cfg::B_STAGE + pb * Cfg::B_PLANE + j * Cfg::B_BOX_BYTES;
+              if constexpr (CG == 2)
+                tma_load_2d_cg2(dst, &tmB, full, n0 + j * Cfg::B_BOX_COLS, pb * p.b_plane_rows + kb * Cfg::BK);
+              else
+                tma_load_2d(dst, &tmB, full, n0 + j * Cfg::B_BOX_COLS, pb * p.b_plane_rows + kb * Cfg::BK);
+            }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(T::C_FMT, T::AB_FMT, /*a_mn=*/0, /*b_mn=*/1, 128, BN);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(T::C_FMT, T::AB_FMT, /*a_mn=*/0, /*b_mn=*/1, Cfg::TILE_M, BN);
       const uint32_t b_lbo = p.dbg_b_lbo ? (uint32_t)p.dbg_b_lbo : (uint32_t)Cfg::B_BOX_BYTES;
       const uint32_t b_sbo = p.dbg_b_sbo ? (uint32_t)p.dbg_b_sbo : (uint32_t)T::B_SBO;
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-       for (int c0 = 0; c0 < num_kb; c0 += p.chunk_kb) {     // one TMEM accumulator per K-chunk
+      for (int w = unit; w < num_items; w += num_units) {
+       const WorkItem it = work_item(w, p, num_kb);
+       for (int c0 = it.kb0; c0 < it.kb1; c0 += p.chunk_kb) {     // one TMEM accumulator per K-chunk
         mbar_wait(bar_tempty + 8 * as, aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
-        const int c1 = min(c0 + p.chunk_kb, num_kb);
+        const int c1 = min(c0 + p.chunk_kb, it.kb1);
         for (int kb = c0; kb < c1; kb++) {
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
@@ -247,13 +287,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                              Cfg::A_SBO, Cfg::A_LAYOUT);
               const uint64_t bd = make_sdesc(b0 + Prod::ib(pr) * Cfg::B_PLANE + k * Cfg::B_KADV, b_lbo,
                                              b_sbo, T::B_LAYOUT);
-              tc_mma<KIND>(d_tmem, ad, bd, idesc, ((kb - c0) | k | pr) != 0 ? 1u : 0u);
+              if constexpr (CG == 2) tc_mma_cg2<KIND>(d_tmem, ad, bd, idesc, ((kb - c0) | k | pr) != 0 ? 1u : 0u);
+              else tc_mma<KIND>(d_tmem, ad, bd, idesc, ((kb - c0) | k | pr) != 0 ? 1u : 0u);
             }
           }
-          tc_commit(bar_empty + 8 * s);            // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if constexpr (CG == 2) tc_commit_cg2(bar_empty + 8 * s, 3); else tc_commit(bar_empty + 8 * s);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        tc_commit(bar_tfull + 8 * as);              // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if constexpr (CG == 2) tc_commit_cg2(bar_tfull + 8 * as, 3); else tc_commit(bar_tfull + 8 * as);
         if (++as == 2) { as = 0; aph ^= 1; }
        }
       }
@@ -267,15 +310,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int VEC_ELEMS = 16 / OB;
     int as = 0;
     uint32_t aph = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const uint32_t tempty_base = CG == 2 ? mapa(bar_tempty, 0) : bar_tempty;   // leader's barrier
+    for (int w = unit; w < num_items; w += num_units) {
+      const WorkItem it = work_item(w, p, num_kb);
       int mb, nb;
-      tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, mb, nb);
-      const int m0 = mb * Cfg::BM + q * 32, n0 = nb * BN;
+      tile_coords(it.tile, p.tiles_m, p.tiles_n, p.group_m, mb, nb);
+      const int m0 = mb * Cfg::TILE_M + (int)cta_rank * Cfg::BM + q * 32, n0 = nb * BN;
+      int* flag = p.flags + ((it.tile - p.full_tiles) * CG + (int)cta_rank) * 4 + q;
+      if (it.part > 0) {                               // wait until parts < it.part are in C
+        if (lane == 0) {
+          const long long t0 = clock64();
+          while (true) {
+            int v;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v == it.part) break;
+            if (clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }
+          }
+        }
+        __syncwarp();
+      }
      // Two-level accumulation (split-precision modes): the tensor core adds into its fp32
      // accumulator with truncation, so a long K chain drifts (measured: error grows ~K).  Each
      // K-chunk gets a fresh TMEM accumulator and is folded into C here with a rounded fp32 add.
-     for (int c0 = 0; c0 < num_kb; c0 += p.chunk_kb) {
-      const bool fold = c0 != 0;
+     for (int c0 = it.kb0; c0 < it.kb1; c0 += p.chunk_kb) {
+      const bool fold = c0 != it.kb0 || it.part > 0;
       mbar_wait(bar_tfull + 8 * as, aph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::ACC_STRIDE;
@@ -287,7 +345,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // folding pass: fetch all eight partial-C vectors first, so their L2 latency overlaps the
         // TMEM load and the staging transpose below
         float4 old[8];
-        if constexpr (std::is_same<OutT, float>::value) {
+        if constexpr (OB == 4) {
           if (fold && vec) {
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -305,7 +363,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (ps == PASSES - 1) {                      // TMEM stage fully drained: hand it back early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_cluster(tempty_base + 8 * as);
+            else mbar_arrive(bar_tempty + 8 * as);
+          }
         }
         OutPack<OutT>::pack(ra, rb, w);
         // registers (row = lane) -> staging, 16-byte chunk index XOR (row & 7): conflict-free both ways
@@ -331,6 +392,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   v.z = __float_as_uint(__uint_as_float(v.z) + old[i].z);
                   v.w = __float_as_uint(__uint_as_float(v.w) + old[i].w);
                 }
+              } else if constexpr (std::is_same<OutT, int32_t>::value) {
+                if (fold) {                           // exact: integer partial sums
+                  v.x += __float_as_uint(old[i].x); v.y += __float_as_uint(old[i].y);
+                  v.z += __float_as_uint(old[i].z); v.w += __float_as_uint(old[i].w);
+                }
               }
               *reinterpret_cast<uint4*>(dst) = v;
             } else {
@@ -340,7 +406,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int e = 0; e < 4; e++)
                   if (col + e < p.N) {
                     if constexpr (std::is_same<OutT, float>::value) {
-                      if (fold) vv[e] = __float_as_uint(__uint_as_float(vv[e]) + reinterpret_cast<const float*>(dst)[e]);
+                      if (fold) vv[e] = __float_as_uint(__uint_as_float(vv[e]) + __ldcg(reinterpret_cast<const float*>(dst) + e));
+                    } else if constexpr (std::is_same<OutT, int32_t>::value) {
+                      if (fold) vv[e] += __ldcg(reinterpret_cast<const uint32_t*>(dst) + e);
                     }
                     reinterpret_cast<uint32_t*>(dst)[e] = vv[e];
                   }
@@ -357,14 +425,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (++as == 2) { as = 0; aph ^= 1; }
      }
+      if (w >= p.full_tiles && p.split > 1) {          // publish this part (the last one re-arms the flag)
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          const int nv = it.part + 1 == p.split ? 0 : it.part + 1;
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(nv) : "memory");
+        }
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync(); else __syncthreads();   // no CTA may exit while its peer still signals it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_cg2<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 

@@ -125,6 +125,11 @@ int b200_convert_f32_to_bf16(const float* dSrc, uint16_t* dDst, size_t count,
 void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes);
 /* Tuning hook: force the tensor-core tile width (128, 192 or 256; 0 = built-in heuristic). */
 void b200_gemm_debug_set_bn(int bn);
+/* Tuning hook: 1 = single-CTA tiles only, 2 = CTA pairs (tcgen05 cta_group::2) always, 0 = auto. */
+void b200_gemm_debug_set_cta_group(int cg);
+/* Tuning hook: 1 (default) = the last partial round of tiles is split along K across the idle
+ * CTAs and folded into C in order; 0 = whole tiles only. */
+void b200_gemm_debug_set_split_tail(int on);
 /* Tuning hook: K extent the tensor core accumulates before the epilogue folds the partial sum
  * into C with a rounded fp32 add (two-level accumulation of the split modes); 0 = whole K. */
 void b200_gemm_debug_set_split_chunk(int bf16x3_k, int bf16x2_k);

@@ -227,7 +227,85 @@ def case_chunk():
                  ms_4096=ms, tflops_4096=2 * N ** 3 / ms / 1e9)
 
 
-CASES = {"chunk": case_chunk, "split": case_split,"strict": case_strict, "bf16": lambda: case_tc("bf16"), "tf32": lambda: case_tc("tf32"),
+def case_pair():
+    """CTA pairs (tcgen05 cta_group::2): parity of every kind against the oracle, then 1-CTA vs 2-CTA time."""
+    import torch
+    o, g = _libs.load_oracle(), _libs.load_pkg()
+    g.lib.b200_gemm_debug_set_cta_group(2)
+    for (m, n, k) in [(256, 256, 64), (256, 256, 256), (384, 512, 1024), (300, 520, 200), (1000, 1100, 2048)]:
+        a, b = _libs.gen_f32(o, m, k, 5), _libs.gen_f32(o, k, n, 6)
+        t = _libs.ref_f64(o, a, b)
+        A, B = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        for mode, name in ((g.F32_TF32, "tf32"), (g.F32_BF16X3, "bf16x3"), (g.F32_BF16X2, "bf16x2")):
+            Cg = g.gemm_f32(A, B, mode=mode).cpu().numpy()
+            emit(case="pair_parity", kind=name, shape=[m, n, k], kernel=g.last_kernel(),
+                 maxrel=float(np.abs(Cg - t).max() / np.abs(t).max()))
+        ab, bb = _libs.round_bf16(o, a), _libs.round_bf16(o, b)
+        tb = _libs.ref_f64(o, ab, bb)
+        Cg = g.gemm_bf16(torch.from_numpy(ab).cuda().bfloat16(), torch.from_numpy(bb).cuda().bfloat16()).cpu().numpy()
+        emit(case="pair_parity", kind="bf16", shape=[m, n, k], kernel=g.last_kernel(),
+             maxrel=float(np.abs(Cg - tb).max() / np.abs(tb).max()))
+        kk, nn = (k + 15) // 16 * 16, (n + 15) // 16 * 16
+        a8, b8 = _libs.gen_s8(o, m, kk, 7), _libs.gen_s8(o, kk, nn, 8)
+        Cg = g.gemm_s8s32(torch.from_numpy(a8).cuda(), torch.from_numpy(b8).cuda()).cpu().numpy()
+        emit(case="pair_parity", kind="s8", shape=[m, nn, kk], kernel=g.last_kernel(),
+             exact=bool(np.array_equal(Cg, _libs.ref_s8(o, a8, b8))))
+    for N in (4096, 8192):
+        A = torch.rand(N, N, device="cuda") - 0.5
+        B = torch.rand(N, N, device="cuda") - 0.5
+        Cc = torch.empty(N, N, device="cuda")
+        Ab, Bb = A.bfloat16(), B.bfloat16()
+        Cb = torch.empty(N, N, device="cuda", dtype=torch.bfloat16)
+        A8 = torch.randint(-127, 128, (N, N), device="cuda", dtype=torch.int8)
+        B8 = torch.randint(-127, 128, (N, N), device="cuda", dtype=torch.int8)
+        C8 = torch.empty(N, N, device="cuda", dtype=torch.int32)
+        for cg, tail in ((1, 0), (1, 1), (2, 0), (2, 1)):
+            g.lib.b200_gemm_debug_set_cta_group(cg)
+            g.lib.b200_gemm_debug_set_split_tail(tail)
+            for name, fn in (("bf16", lambda: g.gemm_bf16(Ab, Bb, out=Cb)),
+                             ("tf32", lambda: g.gemm_f32(A, B, out=Cc, mode=g.F32_TF32)),
+                             ("bf16x3", lambda: g.gemm_f32(A, B, out=Cc, mode=g.F32_BF16X3)),
+                             ("bf16x2", lambda: g.gemm_f32(A, B, out=Cc, mode=g.F32_BF16X2)),
+                             ("s8", lambda: g.gemm_s8s32(A8, B8, out=C8))):
+                ms = time_call(fn)
+                emit(case="pair_time", kind=name, N=N, cg=cg, tail=tail, kernel=g.last_kernel(), ms=ms, tflops=2 * N ** 3 / ms / 1e9)
+    g.lib.b200_gemm_debug_set_cta_group(0)
+    g.lib.b200_gemm_debug_set_split_tail(1)
+
+
+def case_ab():
+    """Noise-robust A/B of the scheduling knobs: interleaved trials, min and median of per-trial means."""
+    import statistics
+    import torch
+    g = _libs.load_pkg()
+    for N in (4096, 8192):
+        A = torch.rand(N, N, device="cuda") - 0.5
+        B = torch.rand(N, N, device="cuda") - 0.5
+        Cc = torch.empty(N, N, device="cuda")
+        Ab, Bb = A.bfloat16(), B.bfloat16()
+        Cf = torch.empty(N, N, device="cuda")
+        Cb = torch.empty(N, N, device="cuda", dtype=torch.bfloat16)
+        kinds = (("bf16_f32out", lambda: g.gemm_bf16(Ab, Bb, out=Cf)), ("bf16_bf16out", lambda: g.gemm_bf16(Ab, Bb, out=Cb)),
+                 ("tf32", lambda: g.gemm_f32(A, B, out=Cc, mode=g.F32_TF32)),
+                 ("bf16x3", lambda: g.gemm_f32(A, B, out=Cc, mode=g.F32_BF16X3)))
+        cfgs = ((1, 0), (1, 1), (2, 0), (2, 1))
+        res = {(k, c): [] for k, _ in kinds for c in cfgs}
+        for trial in range(5):
+            for name, fn in kinds:
+                for cfg in cfgs:
+                    g.lib.b200_gemm_debug_set_cta_group(cfg[0])
+                    g.lib.b200_gemm_debug_set_split_tail(cfg[1])
+                    res[(name, cfg)].append(time_call(fn, reps=20, warm=2))
+        for (name, cfg), v in res.items():
+            emit(case="ab", kind=name, N=N, cg=cfg[0], tail=cfg[1], ms_min=min(v), ms_med=statistics.median(v),
+                 tflops_best=2 * N ** 3 / min(v) / 1e9, tflops_med=2 * N ** 3 / statistics.median(v) / 1e9)
+        ms = [time_call(lambda: torch.matmul(Ab, Bb), reps=20, warm=2) for _ in range(5)]
+        emit(case="ab_cublas_bf16", N=N, tflops_best=2 * N ** 3 / min(ms) / 1e9, tflops_med=2 * N ** 3 / statistics.median(ms) / 1e9)
+    g.lib.b200_gemm_debug_set_cta_group(0)
+    g.lib.b200_gemm_debug_set_split_tail(1)
+
+
+CASES = {"ab": case_ab, "pair": case_pair,"chunk": case_chunk,"split": case_split,"strict": case_strict, "bf16": lambda: case_tc("bf16"), "tf32": lambda: case_tc("tf32"),
          "s8": lambda: case_tc("s8"), "trunc": case_trunc}
 
 if __name__ == "__main__":
