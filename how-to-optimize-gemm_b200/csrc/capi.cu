@@ -173,7 +173,8 @@ int launch_generic(int m, int n, int k, const InT* A, int lda, const InT* B, int
 
 // ---- tensor-core launch -------------------------------------------------------------------
 int g_force_bn = 0;          // test/tuning hook (b200_gemm_debug_set_bn): 0 = heuristic
-int g_force_cg = 0;          // test/tuning hook (b200_gemm_debug_set_cta_group): 0 = auto, 1, 2
+int g_force_cg = 0;
+int g_ffma_halves = 1;      // strict kernel: split the tail round into half tiles (tuning hook)          // test/tuning hook (b200_gemm_debug_set_cta_group): 0 = auto, 1, 2
 
 template <int KIND, int BN, int STAGES, typename OutT, class Prod = ProdSingle, int A_ROW_BYTES = 128, int CG = 1>
 int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_total, int a_plane_rows,
@@ -374,15 +375,23 @@ int launch_ffma(int m, int n, int k, const float* A, int lda, const float* B, in
   p.C = C; p.ldc = ldc; p.M = m; p.N = n; p.K = k;
   p.vec_ok = aligned16(C) && (ldc % 4) == 0;
   p.accumulate = accumulate;
+  p.tiles_m = (m + Cfg::BM - 1) / Cfg::BM;
+  p.tiles_n = (n + Cfg::BN - 1) / Cfg::BN;
+  p.group_m = 8;
+  // 2 CTAs per SM: tiles of the last, at most half-full round are issued as two half tiles each
+  const int tiles = p.tiles_m * p.tiles_n, slots = 2 * g_dev.sms;
+  const int rem = tiles % slots;
+  const bool halves = g_ffma_halves && rem > 0 && 2 * rem <= slots;
+  p.full_tiles = halves ? tiles - rem : tiles;
+  const int ctas = p.full_tiles + 2 * (tiles - p.full_tiles);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_ffma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
     attr_set = true;
   }
-  dim3 grid((n + Cfg::BN - 1) / Cfg::BN, (m + Cfg::BM - 1) / Cfg::BM);
   g_ktimer.begin(st);
-  gemm_ffma_kernel<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  gemm_ffma_kernel<<<ctas, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
   g_ktimer.end(st);
   g_launches++;
   t_last_kernel = "ffma_128x128x32_tma";
@@ -465,6 +474,7 @@ void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes) { g_dbg_b_lbo = lb
 void b200_gemm_debug_set_bn(int bn) { g_force_bn = bn; }
 void b200_gemm_debug_set_cta_group(int cg) { g_force_cg = cg; }
 void b200_gemm_debug_set_split_tail(int on) { g_split_tail = on; }
+void b200_gemm_debug_set_ffma_variant(int v) { g_ffma_halves = v; }
 void b200_gemm_debug_set_split_chunk(int x3_k, int x2_k) { g_split_chunk_k[0] = x3_k; g_split_chunk_k[1] = x2_k; }
 void b200_gemm_debug_kernel_timing(int enable) { g_ktimer.on = enable != 0; g_ktimer.n = 0; }
 int b200_gemm_debug_kernel_time_ms(double* sum_ms) {
