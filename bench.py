@@ -7,8 +7,7 @@
 Workload (BASELINE.json configs[1], headline point): fp32 SGEMM, row-major, M = 4096*N_gpus,
 N = K = 4096.  At 1 GPU this is the 4096^3 point the reference quotes (cuda/output_MMult_cuda_12.m:29);
 at N GPUs C is sharded by row panels (one 4096-row panel per rank, per-GPU work fixed => "weak"),
-B lives on rank 0 and is broadcast over NVLink inside the timed region, pipelined by column panel
-with the GEMM.  A "step" is one such GEMM.  value = 2*M*N*K / max-over-ranks time.
+B lives on rank 0 and is broadcast over NVLink inside the timed region.  A "step" is one such GEMM.  value = 2*M*N*K / max-over-ranks time.
 
 The JSON line also carries: modes (every fp32 precision mode at the same size with its measured
 error against the oracle), sweep (the GFLOP/s-vs-N curve, also written in the reference's
@@ -27,7 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 N0 = 4096                     # headline size
-PANEL = 1024                  # column-panel width of the pipelined broadcast
+BCAST_CHUNKS = 4              # B is broadcast as this many contiguous row blocks
 MODE_NAMES = {0: "strict_ffma", 1: "tf32", 2: "bf16x3", 3: "bf16x2"}
 MODE_DTYPE = {0: "f32", 1: "tf32", 2: "bf16x3(split-f32)", 3: "bf16x2(split-f32)"}
 
@@ -170,6 +169,14 @@ def cpu_baseline(o, budget_s=12.0):
     return out
 
 
+_T0 = time.time()
+
+
+def _phase(name):
+    if os.environ.get("B200_BENCH_TRACE"):
+        print(f"[bench +{time.time() - _T0:6.1f}s] {name}", file=sys.stderr, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -194,12 +201,12 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _phase("torch/nccl up")
     g = _libs.load_pkg()            # raises if libb200gemm.so is missing: no fallback
     mode = args.mode if args.mode >= 0 else g.lib.b200_gemm_default_f32_mode()
     dev = torch.device("cuda", local)
     K = N = N0
     Mloc = N0
-    npan = N // PANEL
 
     # ---- inputs resident in HBM: R rotating sets so consecutive steps never hit a warm L2 --------
     R = 3
@@ -214,26 +221,28 @@ def main():
     if world > 1:
         rowpanel = __import__("importlib").import_module(_libs.PKG + ".rowpanel")
         rp = rowpanel.RowPanelGemm(lambda a, b, out: g.gemm_f32(a, b, out=out, mode=mode), dist, rank, world,
-                                   K, N, PANEL, dev, torch.float32)
+                                   K, N, BCAST_CHUNKS, dev, torch.float32)
 
     def step(i):
         A, B, Cm, _ = sets[i % R]
         if world == 1:
             g.gemm_f32(A, B, out=Cm, mode=mode)
         else:
-            rp.run(A, B, Cm)        # pack + NCCL broadcast of B by column panel, GEMM per panel as it lands
+            rp.run(A, B, Cm)        # NCCL broadcast of B (row chunks, in place), then one GEMM on the local row panel
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()              # nvidia-smi needs ~0.1 s to start: launch it ahead of the warm-up
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        time.sleep(0.15)
     l0 = g.launch_count()
     g.lib.b200_gemm_debug_kernel_timing(1)      # event pair around every dominant-kernel launch, same stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -256,6 +265,7 @@ def main():
     value = flops_step / (ms * 1e-3) / 1e9
     kernel_name = g.last_kernel()
 
+    _phase("timed region done")
     # ---- e2e: the host-pointer plug-in call (9-arg MY_MMult contract, C += A*B), copies inside ----
     e2e_steps = max(3, min(args.steps, 8))
     hA = torch.empty((Mloc, K), dtype=torch.float32).pin_memory().uniform_(-1, 1)
@@ -284,6 +294,7 @@ def main():
             dist.destroy_process_group()
         return
 
+    _phase("e2e done")
     pk = peaks()
     out = {
         "metric": "SGEMM GFLOP/s (square N=4096 point of the 256..4096 sweep)", "value": value, "unit": "GFLOP/s",
@@ -291,7 +302,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": MODE_DTYPE.get(mode, str(mode)), "data": "synthetic",
         "config": {"workload": f"fp32 SGEMM row-major M={Mloc * world} N=K={N0} (BASELINE configs[1], N=4096 point); "
-                               f"C row-panel sharded, B broadcast from rank 0 in {npan} column panels" if world > 1 else
+                               f"C row-panel sharded, B broadcast from rank 0 ({BCAST_CHUNKS} row chunks, NCCL) inside every step" if world > 1 else
                                f"fp32 SGEMM row-major M=N=K={N0} (BASELINE configs[1], N=4096 point)",
                    "precision_mode": MODE_NAMES.get(mode, str(mode)), "kernel": kernel_name,
                    "l2": f"{R} rotating input/output sets of {3 * N0 * N0 * 4 / 1e6:.0f} MB each (> 126 MB L2 between reuses)",
@@ -379,6 +390,7 @@ def main():
             sweep.append([n, round(2.0 * n ** 3 / (s.elapsed_time(e) / 20) / 1e6, 2)])
         out["sweep"] = sweep
         out["cpu_baseline"] = cpu_baseline(o)
+    _phase("extras done")
     print(json.dumps(out))
 
 

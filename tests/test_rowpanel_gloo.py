@@ -1,4 +1,4 @@
-"""The N>1 path on CPU: world_size-2 `gloo` run of the row-panel shard + column-panel broadcast of B
+"""The N>1 path on CPU: world_size-2 `gloo` run of the row-panel shard + row-chunk broadcast of B
 (how-to-optimize-gemm_b200/rowpanel.py).  The local kernel is a host stand-in (the oracle's
 REF_MMult arithmetic) — this checks partitioning and the exchange step, not the CUDA kernels."""
 import os
@@ -39,7 +39,7 @@ def _worker(rank, world, port, M, N, K, panel, out_dir):
         out.copy_(torch.from_numpy(c))
 
     A = torch.from_numpy(L.gen_f32(o, M, K, 100))
-    B = torch.from_numpy(L.gen_f32(o, K, N, 200)) if rank == 0 else None
+    B = torch.from_numpy(L.gen_f32(o, K, N, 200)) if rank == 0 else torch.full((K, N), float("nan"))
     r0, r1 = rowpanel.row_panel(rank, world, M)
     rp = rowpanel.RowPanelGemm(host_gemm, dist, rank, world, K, N, panel, torch.device("cpu"), torch.float32)
     C = torch.full((r1 - r0, N), float("nan"))
@@ -49,7 +49,7 @@ def _worker(rank, world, port, M, N, K, panel, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("M,N,K,panel", [(37, 50, 29, 16), (64, 96, 40, 32)])
+@pytest.mark.parametrize("M,N,K,panel", [(37, 50, 29, 3), (64, 96, 40, 4)])
 def test_rowpanel_world2(tmp_path, oracle, M, N, K, panel):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), M, N, K, panel, str(tmp_path)), nprocs=world, join=True)
@@ -69,5 +69,6 @@ def test_partition_helpers():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
-    assert rowpanel.column_panels(4096, 1024) == [(0, 1024), (1024, 2048), (2048, 3072), (3072, 4096)]
-    assert rowpanel.column_panels(100, 48) == [(0, 48), (48, 96), (96, 100)]
+    assert rowpanel.row_chunks(4096, 4) == [(0, 1024), (1024, 2048), (2048, 3072), (3072, 4096)]
+    assert rowpanel.row_chunks(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    assert rowpanel.row_chunks(2, 8) == [(0, 1), (1, 2)]
