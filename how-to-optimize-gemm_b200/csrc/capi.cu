@@ -224,10 +224,19 @@ int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_tota
     if (split < 1) split = 1;
     if (rem * CG * 4 > 1024) split = 1;               // flag slot capacity
   }
+  // When at least one full round exists, the partial last round is better served by half-width tiles
+  // (no K split, no fold): 2*rem items of half the duration.  Needs BN/2 to be a whole number of
+  // B column blocks per CTA.
+  p.halfn = 0;
+  if (g_split_tail == 1 && tiles >= units_max && rem > 0 && 2 * rem <= units_max &&
+      ((BN / 2 / CG) % Cfg::B_BOX_COLS) == 0 && (BN / 2) % 16 == 0 && (BN / 2) % OutPack<OutT>::COLS == 0) {
+    p.halfn = 1;
+    split = 1;
+  }
   p.split = split;
-  p.full_tiles = split > 1 ? tiles - rem : tiles;
+  p.full_tiles = (split > 1 || p.halfn) ? tiles - rem : tiles;
   p.flags = g_flags + (g_flag_slot++ % 16) * 1024;
-  const int items = p.full_tiles + (tiles - p.full_tiles) * split;
+  const int items = p.full_tiles + (tiles - p.full_tiles) * (p.halfn ? 2 : split);
   const int units = items < units_max ? items : units_max;
   g_ktimer.begin(st);
   if constexpr (CG == 1) {

@@ -73,6 +73,7 @@ struct TcParams {
   // into `split` K-ranges processed by different CTAs/pairs in the last round and folded into C in
   // order (part p waits for flag == p on its 32-row strip, adds, then publishes p+1).
   int full_tiles, split;
+  int halfn;               // 1: tail tiles are issued as two half-width (BN/2) tiles instead of K parts
   int* flags;              // [tail tile][cta rank][epilogue warp], zero between launches
   int dbg_b_lbo, dbg_b_sbo;  // 0 = defaults (probe hook, see b200_gemm_debug_set_b_desc)
 };
@@ -120,11 +121,18 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
   nb = r / rows;
 }
 
-struct WorkItem { int tile, part, kb0, kb1; };
+struct WorkItem { int tile, part, kb0, kb1, nsub, bn; };
+template <int BN>
 __device__ __forceinline__ WorkItem work_item(int w, const TcParams& p, int num_kb) {
   WorkItem it;
+  it.nsub = 0; it.bn = BN;
   if (w < p.full_tiles) { it.tile = w; it.part = 0; it.kb0 = 0; it.kb1 = num_kb; return it; }
   const int r = w - p.full_tiles;
+  if (p.halfn) {        // tail round as half-width tiles: same K chain, no cross-CTA reduction
+    it.tile = p.full_tiles + (r >> 1); it.nsub = r & 1; it.bn = BN / 2;
+    it.part = 0; it.kb0 = 0; it.kb1 = num_kb;
+    return it;
+  }
   it.tile = p.full_tiles + r / p.split;
   it.part = r - (r / p.split) * p.split;
   it.kb0 = (int)((long long)num_kb * it.part / p.split);
@@ -218,7 +226,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (s_tmem_ptr - smem_base));
 
   const int num_tiles = p.tiles_m * p.tiles_n;
-  const int num_items = p.full_tiles + (num_tiles - p.full_tiles) * p.split;
+  const int num_items = p.full_tiles + (num_tiles - p.full_tiles) * (p.halfn ? 2 : p.split);
   const int num_kb = (p.K + Cfg::BK - 1) / Cfg::BK;
 
   if (warp == 0) {
@@ -227,16 +235,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0;
       for (int w = unit; w < num_items; w += num_units) {
-        const WorkItem it = work_item(w, p, num_kb);
+        const WorkItem it = work_item<BN>(w, p, num_kb);
         int mb, nb;
         tile_coords(it.tile, p.tiles_m, p.tiles_n, p.group_m, mb, nb);
         // this CTA's slice of the unit: its 128 rows of A, its BN/CG columns of B
-        const int m0 = mb * Cfg::TILE_M + (int)cta_rank * Cfg::BM, n0 = nb * BN + (int)cta_rank * Cfg::BN_CTA;
+        const int bn_cta = it.bn / CG;
+        const int boxes = bn_cta / Cfg::B_BOX_COLS;       // B column blocks this CTA stages per plane
+        const uint32_t tx_bytes = CG * (Cfg::A_STAGE + Prod::NPB * boxes * Cfg::B_BOX_BYTES);
+        const int m0 = mb * Cfg::TILE_M + (int)cta_rank * Cfg::BM, n0 = nb * BN + it.nsub * it.bn + (int)cta_rank * bn_cta;
         for (int kb = it.kb0; kb < it.kb1; kb++) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           // bytes from both CTAs complete on the LEADER's full barrier; only the leader arms it
           const uint32_t full = CG == 2 ? mapa(bar_full + 8 * s, 0) : bar_full + 8 * s;
-          if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::TX_BYTES);
+          if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, tx_bytes);
 #pragma unroll
           for (int pa = 0; pa < Prod::NPA; pa++) {
             const uint32_t dst = sA + s * Cfg::A_STAGE + pa * Cfg::A_PLANE;
@@ -247,6 +258,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int pb = 0; pb < Prod::NPB; pb++)
 #pragma unroll
             for (int j = 0; j < Cfg::B_BOXES; j++) {
+              if (j >= boxes) break;
               const uint32_t dst = sB + s * Cfg::B_STAGE + pb * Cfg::B_PLANE + j * Cfg::B_BOX_BYTES;
               if constexpr (CG == 2)
                 tma_load_2d_cg2(dst, &tmB, full, n0 + j * Cfg::B_BOX_COLS, pb * p.b_plane_rows + kb * Cfg::BK);
@@ -260,7 +272,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc(T::C_FMT, T::AB_FMT, /*a_mn=*/0, /*b_mn=*/1, Cfg::TILE_M, BN);
+
       const uint32_t b_lbo = p.dbg_b_lbo ? (uint32_t)p.dbg_b_lbo : (uint32_t)Cfg::B_BOX_BYTES;
       const uint32_t b_sbo = p.dbg_b_sbo ? (uint32_t)p.dbg_b_sbo : (uint32_t)T::B_SBO;
       int s = 0;
@@ -268,7 +280,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int as = 0;
       uint32_t aph = 0;
       for (int w = unit; w < num_items; w += num_units) {
-       const WorkItem it = work_item(w, p, num_kb);
+       const WorkItem it = work_item<BN>(w, p, num_kb);
+       const uint32_t idesc = make_idesc(T::C_FMT, T::AB_FMT, /*a_mn=*/0, /*b_mn=*/1, Cfg::TILE_M, it.bn);
        for (int c0 = it.kb0; c0 < it.kb1; c0 += p.chunk_kb) {     // one TMEM accumulator per K-chunk
         mbar_wait(bar_tempty + 8 * as, aph ^ 1);
         tc_fence_after();
@@ -306,16 +319,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;                          // TMEM lane quadrant this warp may read
     uint8_t* stg = smem_gen + (sEpi - smem_base) + q * 4096;   // 32 rows x 128 B, chunk-swizzled
     constexpr int COLS = OutPack<OutT>::COLS;
-    constexpr int PASSES = BN / COLS;
     constexpr int VEC_ELEMS = 16 / OB;
     int as = 0;
     uint32_t aph = 0;
     const uint32_t tempty_base = CG == 2 ? mapa(bar_tempty, 0) : bar_tempty;   // leader's barrier
     for (int w = unit; w < num_items; w += num_units) {
-      const WorkItem it = work_item(w, p, num_kb);
+      const WorkItem it = work_item<BN>(w, p, num_kb);
       int mb, nb;
       tile_coords(it.tile, p.tiles_m, p.tiles_n, p.group_m, mb, nb);
-      const int m0 = mb * Cfg::TILE_M + (int)cta_rank * Cfg::BM + q * 32, n0 = nb * BN;
+      const int m0 = mb * Cfg::TILE_M + (int)cta_rank * Cfg::BM + q * 32, n0 = nb * BN + it.nsub * it.bn;
+      const int passes = it.bn / COLS;
       int* flag = p.flags + ((it.tile - p.full_tiles) * CG + (int)cta_rank) * 4 + q;
       if (it.part > 0) {                               // wait until parts < it.part are in C
         if (lane == 0) {
@@ -338,7 +351,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::ACC_STRIDE;
 #pragma unroll 1
-      for (int ps = 0; ps < PASSES; ps++) {
+      for (int ps = 0; ps < passes; ps++) {
         const int chunk = lane & 7;
         const int col = n0 + ps * COLS + chunk * VEC_ELEMS;
         const bool vec = p.vec_ok && col + VEC_ELEMS <= p.N;
@@ -360,7 +373,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_32x32b_x32(t_addr + ps * (COLS == 64 ? 64 : 32), ra);
         if constexpr (COLS == 64) tmem_ld_32x32b_x32(t_addr + ps * 64 + 32, rb);
         tmem_ld_wait();
-        if (ps == PASSES - 1) {                      // TMEM stage fully drained: hand it back early
+        if (ps == passes - 1) {                      // TMEM stage fully drained: hand it back early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {

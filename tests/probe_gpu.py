@@ -288,7 +288,7 @@ def case_ab():
         kinds = (("bf16_f32out", lambda: g.gemm_bf16(Ab, Bb, out=Cf)), ("bf16_bf16out", lambda: g.gemm_bf16(Ab, Bb, out=Cb)),
                  ("tf32", lambda: g.gemm_f32(A, B, out=Cc, mode=g.F32_TF32)),
                  ("bf16x3", lambda: g.gemm_f32(A, B, out=Cc, mode=g.F32_BF16X3)))
-        cfgs = ((1, 0), (1, 1), (2, 0), (2, 1))
+        cfgs = ((2, 0), (2, 1), (2, 2), (1, 0), (1, 1))
         res = {(k, c): [] for k, _ in kinds for c in cfgs}
         for trial in range(5):
             for name, fn in kinds:
