@@ -185,6 +185,9 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--mode", type=int, default=-1, help="fp32 precision mode of the headline (default: library default)")
     ap.add_argument("--no-extras", action="store_true", help="skip sweep / modes / cpu_baseline (quick runs)")
+    ap.add_argument("--workload", default="headline", choices=["headline", "c5"],
+                    help="headline: M=4096*gpus, N=K=4096 (weak).  c5: BASELINE configs[4], M=N=K=16384 "
+                         "row-panel sharded over the ranks (strong); not the driver's default")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -207,9 +210,14 @@ def main():
     dev = torch.device("cuda", local)
     K = N = N0
     Mloc = N0
+    scaling = "weak"
+    if args.workload == "c5":
+        K = N = 16384
+        Mloc = 16384 // world
+        scaling = "strong"
 
     # ---- inputs resident in HBM: R rotating sets so consecutive steps never hit a warm L2 --------
-    R = 3
+    R = 3 if args.workload == "headline" else 1     # c5 operands (1 GiB each) exceed L2 on their own
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     sets = []
     for _ in range(R):
@@ -267,7 +275,7 @@ def main():
 
     _phase("timed region done")
     # ---- e2e: the host-pointer plug-in call (9-arg MY_MMult contract, C += A*B), copies inside ----
-    e2e_steps = max(3, min(args.steps, 8))
+    e2e_steps = max(3, min(args.steps, 8)) if args.workload == "headline" else 2
     hA = torch.empty((Mloc, K), dtype=torch.float32).pin_memory().uniform_(-1, 1)
     hB = torch.empty((K, N), dtype=torch.float32).pin_memory().uniform_(-1, 1)
     hC = torch.zeros((Mloc, N), dtype=torch.float32).pin_memory()
@@ -299,9 +307,9 @@ def main():
     out = {
         "metric": "SGEMM GFLOP/s (square N=4096 point of the 256..4096 sweep)", "value": value, "unit": "GFLOP/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": MODE_DTYPE.get(mode, str(mode)), "data": "synthetic",
-        "config": {"workload": f"fp32 SGEMM row-major M={Mloc * world} N=K={N0} (BASELINE configs[1], N=4096 point); "
+        "config": {"workload": f"fp32 SGEMM row-major M={Mloc * world} N=K={N} (BASELINE configs[{1 if args.workload == 'headline' else 4}]); "
                                f"C row-panel sharded, B broadcast from rank 0 ({BCAST_CHUNKS} row chunks, NCCL) inside every step" if world > 1 else
                                f"fp32 SGEMM row-major M=N=K={N0} (BASELINE configs[1], N=4096 point)",
                    "precision_mode": MODE_NAMES.get(mode, str(mode)), "kernel": kernel_name,
@@ -312,7 +320,7 @@ def main():
     }
     # roofline of the dominant kernel: its own launch durations (CUDA events on the launching stream,
     # recorded inside the timed region); algorithmic flops = 2*M*N*K, no credit for the 6 split passes
-    if world == 1:
+    if world == 1 and args.workload == "headline":
         kern_ms = kern_ms_sum / max(kern_launches, 1)
         achieved = 2.0 * N0 ** 3 / (kern_ms * 1e-3) / 1e12
         out["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
@@ -336,7 +344,7 @@ def main():
             except Exception:
                 pass
 
-    if not args.no_extras and world == 1:
+    if not args.no_extras and world == 1 and args.workload == "headline":
         o = _libs.load_oracle()
         A, B, Cm, _ = sets[0]
         # ---- every precision mode at the headline size, with its error against the oracle --------
