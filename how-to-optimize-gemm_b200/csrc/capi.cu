@@ -173,6 +173,7 @@ int launch_generic(int m, int n, int k, const InT* A, int lda, const InT* B, int
 
 // ---- tensor-core launch -------------------------------------------------------------------
 int g_force_bn = 0;          // test/tuning hook (b200_gemm_debug_set_bn): 0 = heuristic
+int g_group_rows = 0;         // tuning hook: rows per raster group of the tensor-core kernels (0 = 2048)
 int g_force_cg = 0;
 int g_ffma_halves = 1;      // strict kernel: split the tail round into half tiles (tuning hook)          // test/tuning hook (b200_gemm_debug_set_cta_group): 0 = auto, 1, 2
 
@@ -196,7 +197,8 @@ int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_tota
   p.C = C; p.ldc = ldc; p.M = m; p.N = n; p.K = k;
   p.tiles_m = (m + Cfg::TILE_M - 1) / Cfg::TILE_M;
   p.tiles_n = (n + BN - 1) / BN;
-  p.group_m = 16 / CG;     // 2048 rows of A per raster group either way
+  p.group_m = (g_group_rows > 0 ? g_group_rows : 2048) / Cfg::TILE_M;     // rows of A per raster group
+  if (p.group_m < 1) p.group_m = 1;
   constexpr int OB = OutBytes<OutT>::V;
   p.vec_ok = aligned16(C) && ((long long)ldc * OB) % 16 == 0;
   p.a_plane_rows = a_plane_rows; p.b_plane_rows = b_plane_rows;
@@ -433,8 +435,13 @@ int gemm_f32_impl(int m, int n, int k, const float* dA, int lda, const float* dB
   rc = ensure_device();
   if (rc) return rc;
   if (k == 0) return accumulate ? 0 : launch_zero<float>(m, n, dC, ldc, st);
+  const bool was_auto = mode == B200_F32_AUTO;
   mode = resolve_f32_mode(mode);
   const bool tma = tma_ok(dA, lda, dB, ldb, 4);
+  // AUTO on a small problem: the split path costs three launches (two pre-pass + GEMM) and cannot
+  // fill 74 CTA pairs; below ~1024^3 the single-launch strict FFMA2 kernel is both faster (measured:
+  // 40 vs 33.5 TFLOP/s at 1024^3, 9.2 vs 6.9 at 512^3) and bit-exact against the reference oracle.
+  if (was_auto && mode == B200_F32_BF16X3 && tma && (double)m * n * k <= 1.1e9) mode = B200_F32_STRICT;
   switch (mode) {
     case B200_F32_STRICT:
       if (tma) return launch_ffma(m, n, k, dA, lda, dB, ldb, dC, ldc, accumulate, st);
@@ -483,6 +490,7 @@ void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes) { g_dbg_b_lbo = lb
 void b200_gemm_debug_set_bn(int bn) { g_force_bn = bn; }
 void b200_gemm_debug_set_cta_group(int cg) { g_force_cg = cg; }
 void b200_gemm_debug_set_split_tail(int on) { g_split_tail = on; }
+void b200_gemm_debug_set_group_rows(int rows) { g_group_rows = rows; }
 void b200_gemm_debug_set_ffma_variant(int v) { g_ffma_halves = v; }
 void b200_gemm_debug_set_split_chunk(int x3_k, int x2_k) { g_split_chunk_k[0] = x3_k; g_split_chunk_k[1] = x2_k; }
 void b200_gemm_debug_kernel_timing(int enable) { g_ktimer.on = enable != 0; g_ktimer.n = 0; }
