@@ -27,8 +27,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 N0 = 4096                     # headline size
 BCAST_CHUNKS = 4              # B is broadcast as this many contiguous row blocks
-MODE_NAMES = {0: "strict_ffma", 1: "tf32", 2: "bf16x3", 3: "bf16x2"}
-MODE_DTYPE = {0: "f32", 1: "tf32", 2: "bf16x3(split-f32)", 3: "bf16x2(split-f32)"}
+MODE_NAMES = {0: "strict_ffma", 1: "tf32", 2: "bf16x3", 3: "bf16x2", 5: "f16x2_scaled"}
+MODE_DTYPE = {0: "f32", 1: "tf32", 2: "bf16x3(split-f32)", 3: "bf16x2(split-f32)", 5: "f16x2(scaled split-f32)"}
 
 
 def peaks():
@@ -327,8 +327,8 @@ def main():
                            "frac": achieved / pk["bf16_tflops"], "traffic": None,
                            "kernel_ms": kern_ms, "kernel_launches_timed": kern_launches,
                            "kernel_share_of_step": kern_ms / ms,
-                           "tensor_pipe_flops_per_launch": 2.0 * N0 ** 3 * {2: 6, 3: 3}.get(mode, 1),
-                           "tensor_pipe_frac": achieved * {2: 6, 3: 3}.get(mode, 1) / ({1: 0.5}.get(mode, 1.0) * pk["bf16_tflops"]),
+                           "tensor_pipe_flops_per_launch": 2.0 * N0 ** 3 * {2: 6, 3: 3, 5: 3}.get(mode, 1),
+                           "tensor_pipe_frac": achieved * {2: 6, 3: 3, 5: 3}.get(mode, 1) / ({1: 0.5}.get(mode, 1.0) * pk["bf16_tflops"]),
                            "peak_source": pk["source"] + ", burst bf16; sustained " + str(pk["bf16_tflops_sustained"]),
                            "frac_of_sustained": achieved / pk["bf16_tflops_sustained"] if pk["bf16_tflops_sustained"] else None,
                            "algorithmic_flops_per_launch": 2.0 * N0 ** 3,

@@ -16,7 +16,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200gemm.so")
 
-F32_STRICT, F32_TF32, F32_BF16X3, F32_BF16X2, F32_AUTO = 0, 1, 2, 3, 4
+F32_STRICT, F32_TF32, F32_BF16X3, F32_BF16X2, F32_AUTO, F32_F16X2 = 0, 1, 2, 3, 4, 5
 OUT_F32, OUT_BF16 = 0, 1
 
 EXPORTS = [

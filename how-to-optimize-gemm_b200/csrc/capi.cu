@@ -180,10 +180,12 @@ int g_ffma_halves = 1;      // strict kernel: split the tail round into half til
 template <int KIND, int BN, int STAGES, typename OutT, class Prod = ProdSingle, int A_ROW_BYTES = 128, int CG = 1>
 int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_total, int a_plane_rows,
               const void* B, long long ldb, int b_rows_total, int b_plane_rows, void* C, int ldc,
-              cudaStream_t st, const char* name, int chunk_k = 0) {
+              cudaStream_t st, const char* name, int chunk_k = 0, const float* row_max = nullptr,
+              const float* col_max = nullptr) {
   using Cfg = TcConfig<KIND, BN, STAGES, Prod, A_ROW_BYTES, CG>;
   using T = KindTraits<KIND>;
   constexpr CUtensorMapDataType dt = KIND == KIND_F16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                   : KIND == KIND_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                    : KIND == KIND_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                                        : CU_TENSOR_MAP_DATA_TYPE_UINT8;
   CUtensorMap tmA, tmB;
@@ -205,6 +207,7 @@ int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_tota
   p.chunk_kb = chunk_k > 0 ? (chunk_k + Cfg::BK - 1) / Cfg::BK : (k + Cfg::BK - 1) / Cfg::BK;
   if (p.chunk_kb < 1) p.chunk_kb = 1;
   p.dbg_b_lbo = g_dbg_b_lbo; p.dbg_b_sbo = g_dbg_b_sbo;
+  p.row_max = row_max; p.col_max = col_max;
   auto kern = gemm_tc_kernel<KIND, BN, STAGES, OutT, Prod, A_ROW_BYTES, CG>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -374,6 +377,54 @@ int gemm_f32_split(int m, int n, int k, const float* A, int lda, const float* B,
   }
 }
 
+// B200_F32_F16X2: scaled fp16 split, 3 products.  Row maxima of A and column maxima of B give exact
+// power-of-two scalings that bring every operand into [-1, 1] (fp16 has 5 exponent bits); the
+// epilogue multiplies them back.  Launches: memset, 2 x absmax, 2 x split, GEMM.
+int gemm_f32_split_f16(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                       cudaStream_t st) {
+  constexpr int NP = 2;
+  const long long pka = ((long long)k + 7) & ~7LL, pnb = ((long long)n + 7) & ~7LL;
+  const int kp = (k + 31) & ~31;
+  const size_t a_bytes = (size_t)NP * m * pka * 2, b_bytes = (size_t)NP * kp * pnb * 2;
+  const size_t a_off = (a_bytes + 1023) & ~(size_t)1023;
+  const size_t b_off = (a_off + b_bytes + 1023) & ~(size_t)1023;       // row maxima, then column maxima
+  const size_t c_off = b_off + (((size_t)m * 4 + 1023) & ~(size_t)1023);
+  const size_t total = c_off + (size_t)n * 4;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_split_ws.bytes < total) {
+      if (g_split_ws.p) { cudaStreamSynchronize(st); cudaFree(g_split_ws.p); }
+      g_split_ws.p = nullptr; g_split_ws.bytes = 0;
+      cudaError_t e = cudaMalloc(&g_split_ws.p, total);
+      if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+      g_split_ws.bytes = total;
+    }
+  }
+  uint8_t* base = reinterpret_cast<uint8_t*>(g_split_ws.p);
+  uint16_t* pA = reinterpret_cast<uint16_t*>(base);
+  uint16_t* pB = reinterpret_cast<uint16_t*>(base + a_off);
+  float* rmax = reinterpret_cast<float*>(base + b_off);
+  float* cmax = reinterpret_cast<float*>(base + c_off);
+  cudaError_t e = cudaMemsetAsync(cmax, 0, (size_t)n * 4, st);
+  if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+  const int blocks = g_dev.sms * 8;
+  row_absmax_kernel<<<blocks, 256, 0, st>>>(A, lda, m, k, rmax);
+  col_absmax_kernel<<<dim3((n + 255) / 256, (k + 63) / 64), 256, 0, st>>>(B, ldb, k, n, reinterpret_cast<unsigned int*>(cmax));
+  split_planes_f16_kernel<true><<<blocks, 256, 0, st>>>(A, lda, m, k, rmax, pA, pka, m);
+  split_planes_f16_kernel<false><<<blocks, 256, 0, st>>>(B, ldb, k, n, cmax, pB, pnb, kp);
+  g_launches += 4;
+  int rc = last_launch_status();
+  if (rc) return rc;
+  if (use_pair(m, n))
+    return launch_tc<KIND_FP16, 256, 6, float, ProdX2, 64, 2>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st,
+                                                              "tc_f16x2_2cta_256x256", g_split_chunk_k[1], rmax, cmax);
+  if (pick_bn(m, n, true, false) == 256)
+    return launch_tc<KIND_FP16, 256, 4, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st,
+                                                           "tc_f16x2_128x256", g_split_chunk_k[1], rmax, cmax);
+  return launch_tc<KIND_FP16, 128, 6, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st,
+                                                         "tc_f16x2_128x128", g_split_chunk_k[1], rmax, cmax);
+}
+
 int launch_ffma(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                 int accumulate, cudaStream_t st) {
   using Cfg = FfmaCfg;
@@ -419,7 +470,7 @@ int resolve_f32_mode(int mode) {
     if (d < 0) {
       const char* e = getenv("B200GEMM_F32_MODE");
       d = e ? atoi(e) : B200_F32_BF16X3;
-      if (d < 0 || d >= B200_F32_AUTO) d = B200_F32_BF16X3;
+      if (d < 0 || d == B200_F32_AUTO || d > B200_F32_F16X2) d = B200_F32_BF16X3;
       g_default_f32_mode.store(d);
     }
     return d;
@@ -456,6 +507,9 @@ int gemm_f32_impl(int m, int n, int k, const float* dA, int lda, const float* dB
     case B200_F32_BF16X2:
       if (accumulate) return B200_ERR_UNSUPPORTED;
       return gemm_f32_split<2>(m, n, k, dA, lda, dB, ldb, dC, ldc, st);
+    case B200_F32_F16X2:
+      if (accumulate) return B200_ERR_UNSUPPORTED;
+      return gemm_f32_split_f16(m, n, k, dA, lda, dB, ldb, dC, ldc, st);
     default:
       return B200_ERR_UNSUPPORTED;
   }
@@ -484,7 +538,7 @@ const char* b200_gemm_last_kernel(void) { return t_last_kernel; }
 unsigned long long b200_gemm_launch_count(void) { return g_launches.load(); }
 int b200_gemm_default_f32_mode(void) { return resolve_f32_mode(B200_F32_AUTO); }
 void b200_gemm_set_default_f32_mode(int mode) {
-  if (mode >= 0 && mode < B200_F32_AUTO) g_default_f32_mode.store(mode);
+  if (mode >= 0 && mode != B200_F32_AUTO && mode <= B200_F32_F16X2) g_default_f32_mode.store(mode);
 }
 void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes) { g_dbg_b_lbo = lbo_bytes; g_dbg_b_sbo = sbo_bytes; }
 void b200_gemm_debug_set_bn(int bn) { g_force_bn = bn; }

@@ -25,6 +25,8 @@
 // TMEM full/empty (two accumulator stages, so the epilogue of tile i overlaps the mainloop of i+1),
 // and the static persistent tile schedule.
 #pragma once
+#include <cuda_fp16.h>
+#include <string.h>
 #include <type_traits>
 
 #include "ptx.cuh"
@@ -38,6 +40,7 @@ template <int KIND> struct KindTraits;
 // Measured on B200: the 16-byte-atom layout with kind::tf32 returns all-zero accumulators.
 template <> struct KindTraits<KIND_F16>  { static constexpr int ELEM = 2, UMMA_K = 16, AB_FMT = 1, C_FMT = 1, B_LAYOUT = 2, B_SBO = 1024; };
 template <> struct KindTraits<KIND_TF32> { static constexpr int ELEM = 4, UMMA_K = 8,  AB_FMT = 2, C_FMT = 1, B_LAYOUT = 1, B_SBO = 512; };
+template <> struct KindTraits<KIND_FP16> { static constexpr int ELEM = 2, UMMA_K = 16, AB_FMT = 0, C_FMT = 1, B_LAYOUT = 2, B_SBO = 1024; };
 template <> struct KindTraits<KIND_I8>   { static constexpr int ELEM = 1, UMMA_K = 32, AB_FMT = 1, C_FMT = 2, B_LAYOUT = 2, B_SBO = 1024; };
 
 // Plane products issued per k-step.  Single: plain GEMM.  X3: a=a1+a2+a3, b likewise, all terms down
@@ -75,6 +78,10 @@ struct TcParams {
   int full_tiles, split;
   int halfn;               // 1: tail tiles are issued as two half-width (BN/2) tiles instead of K parts
   int* flags;              // [tail tile][cta rank][epilogue warp], zero between launches
+  // Scaled split mode (B200_F32_F16X2): operands were multiplied by 2^-e(row) / 2^-e(col) before the
+  // fp16 split; the epilogue multiplies back by 2^e(row) * 2^e(col), exact.  Null = no scaling.
+  const float* row_max;    // [M] max |A(i,:)|
+  const float* col_max;    // [N] max |B(:,j)|
   int dbg_b_lbo, dbg_b_sbo;  // 0 = defaults (probe hook, see b200_gemm_debug_set_b_desc)
 };
 
@@ -119,6 +126,26 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
   const int r = t - g * per_group;
   mb = first_m + r % rows;
   nb = r / rows;
+}
+
+// 2^e (inverse = false) or 2^-e (inverse = true) with e such that maxv * 2^-e lies in [0.5, 1);
+// 1 for zero, denormal, inf or NaN maxima; |e| clamped so both factors stay normal.
+__host__ __device__ __forceinline__ float pow2_factor(float maxv, bool inverse) {
+  uint32_t bits;
+#ifdef __CUDA_ARCH__
+  bits = __float_as_uint(maxv);
+#else
+  memcpy(&bits, &maxv, 4);
+#endif
+  const int ef = (int)((bits >> 23) & 0xFF);
+  int e = (ef == 0 || ef == 255) ? 0 : ef - 126;
+  e = e > 96 ? 96 : (e < -96 ? -96 : e);
+  const uint32_t out = (uint32_t)(127 + (inverse ? -e : e)) << 23;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(out);
+#else
+  float f; memcpy(&f, &out, 4); return f;
+#endif
 }
 
 struct WorkItem { int tile, part, kb0, kb1, nsub, bn; };
@@ -390,11 +417,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
         // staging -> global: 8 lanes cover one 128-byte row segment, 4 rows per instruction
+        float cs[4] = {1.f, 1.f, 1.f, 1.f};
+        if constexpr (std::is_same<OutT, float>::value) {
+          if (p.col_max != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+              if (col + e < p.N) cs[e] = pow2_factor(__ldg(p.col_max + col + e), false);
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 8; i++) {
           const int row = i * 4 + (lane >> 3);
           const int gm = m0 + row;
           uint4 v = *reinterpret_cast<const uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4));
+          if constexpr (std::is_same<OutT, float>::value) {
+            if (p.row_max != nullptr && gm < p.M) {      // undo the operand scaling: exact powers of two
+              const float rs = pow2_factor(__ldg(p.row_max + gm), false);
+              v.x = __float_as_uint(__uint_as_float(v.x) * (rs * cs[0]));
+              v.y = __float_as_uint(__uint_as_float(v.y) * (rs * cs[1]));
+              v.z = __float_as_uint(__uint_as_float(v.z) * (rs * cs[2]));
+              v.w = __float_as_uint(__uint_as_float(v.w) * (rs * cs[3]));
+            }
+          }
           if (gm < p.M) {
             uint8_t* dst = reinterpret_cast<uint8_t*>(p.C) + ((long long)gm * p.ldc + col) * OB;
             if (vec) {
@@ -497,6 +541,66 @@ __global__ void split_planes_kernel(const float* __restrict__ src, long long ld,
       uint2 o = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
       *reinterpret_cast<uint2*>(dst + ((long long)pl * plane_rows + r) * dld + c) = o;
     }
+  }
+}
+
+
+// ---- scaled fp16 split (B200_F32_F16X2) ------------------------------------------------------------
+// x' = x * 2^-e (e from the row maximum of A / the column maximum of B, so |x'| <= 1), then
+// x' = h1 + h2 with h1 = fp16(x'), h2 = fp16(x' - h1): 22 significant bits; h2 may be an fp16
+// subnormal (absolute quantum 2^-24 relative to the row/column scale).
+__global__ void row_absmax_kernel(const float* __restrict__ src, long long ld, int rows, int cols,
+                                  float* __restrict__ out) {
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const float* s = src + (long long)r * ld;
+    float mx = 0.f;
+    for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, fabsf(s[c]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) out[r] = mx;
+  }
+}
+// out must be zeroed; non-negative floats order like their bit patterns, so atomicMax on uint works
+__global__ void col_absmax_kernel(const float* __restrict__ src, long long ld, int rows, int cols,
+                                  unsigned int* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const int r0 = blockIdx.y * 64, r1 = min(r0 + 64, rows);
+  float mx = 0.f;
+  for (int r = r0; r < r1; r++) mx = fmaxf(mx, fabsf(src[(long long)r * ld + c]));
+  atomicMax(out + c, __float_as_uint(mx));
+}
+template <bool BY_ROW>
+__global__ void split_planes_f16_kernel(const float* __restrict__ src, long long ld, int rows, int cols,
+                                        const float* __restrict__ maxv, uint16_t* __restrict__ dst,
+                                        long long dld, int plane_rows) {
+  const int cgroups = (int)(dld >> 2);
+  const long long total = (long long)plane_rows * cgroups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cgroups);
+    const int c = (int)(i - (long long)r * cgroups) * 4;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < rows) {
+      const float rowf = BY_ROW ? pow2_factor(maxv[r], true) : 1.f;
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        if (c + e < cols) x[e] = src[(long long)r * ld + c + e] * (BY_ROW ? rowf : pow2_factor(maxv[c + e], true));
+    }
+    uint16_t h1[4], h2[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const __half a = __float2half_rn(x[e]);
+      const __half b = __float2half_rn(x[e] - __half2float(a));
+      h1[e] = __half_as_ushort(a);
+      h2[e] = __half_as_ushort(b);
+    }
+    *reinterpret_cast<uint2*>(dst + (long long)r * dld + c) =
+        make_uint2((uint32_t)h1[0] | ((uint32_t)h1[1] << 16), (uint32_t)h1[2] | ((uint32_t)h1[3] << 16));
+    *reinterpret_cast<uint2*>(dst + ((long long)plane_rows + r) * dld + c) =
+        make_uint2((uint32_t)h2[0] | ((uint32_t)h2[1] << 16), (uint32_t)h2[2] | ((uint32_t)h2[3] << 16));
   }
 }
 

@@ -98,13 +98,13 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
                : "memory");
 }
 
-enum MmaKind { KIND_F16 = 0, KIND_TF32 = 1, KIND_I8 = 2 };
+enum MmaKind { KIND_F16 = 0 /*bf16 operands*/, KIND_TF32 = 1, KIND_I8 = 2, KIND_FP16 = 3 /*fp16 operands, kind::f16*/ };
 
 // D[tmem] (+)= A[smem desc] * B[smem desc]; single-thread issue.
 template <int KIND>
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
                                        uint32_t idesc, uint32_t accumulate) {
-  if constexpr (KIND == KIND_F16) {
+  if constexpr (KIND == KIND_F16 || KIND == KIND_FP16) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -196,7 +196,7 @@ __device__ __forceinline__ void tc_commit_cg2(uint32_t bar, uint16_t cta_mask) {
 template <int KIND>
 __device__ __forceinline__ void tc_mma_cg2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
                                            uint32_t idesc, uint32_t accumulate) {
-  if constexpr (KIND == KIND_F16) {
+  if constexpr (KIND == KIND_F16 || KIND == KIND_FP16) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"

@@ -67,6 +67,39 @@ TOL_X3 = 1e-5      # split-bf16 x3 with two-level accumulation: fp32-class (stri
 TOL_X2 = 4e-5      # split-bf16 x2: dropped a2*b2 term, ~2^-17 relative
 
 
+TOL_F16X2 = 1e-5   # scaled split-fp16, 22-bit operands: normwise fp32-class
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES + [(1000, 1100, 4096), (260, 200, 1500)])
+def test_f32_split_f16_scaled(gemm, oracle, m, n, k):
+    a, b = _libs.gen_f32(oracle, m, k, 35), _libs.gen_f32(oracle, k, n, 36)
+    c = gemm.gemm_f32(cuda(a), cuda(b), mode=gemm.F32_F16X2).cpu().numpy()
+    assert gemm.last_kernel().startswith("tc_f16x2"), gemm.last_kernel()
+    t = _libs.ref_f64(oracle, a, b)
+    assert rel(c, t) <= TOL_F16X2, (gemm.last_kernel(), rel(c, t))
+
+
+def test_f32_split_f16_dynamic_range(gemm, oracle):
+    """fp16 has 5 exponent bits: the mode must survive rows of A / columns of B spread over 2^+-20
+    (power-of-two row/column scaling is exact, so the scaled result must track the unscaled one)."""
+    m, n, k = 384, 520, 1024
+    rng = np.random.default_rng(7)
+    a0, b0 = _libs.gen_f32(oracle, m, k, 37), _libs.gen_f32(oracle, k, n, 38)
+    rs = np.exp2(rng.integers(-20, 21, m)).astype(np.float32)
+    cs = np.exp2(rng.integers(-20, 21, n)).astype(np.float32)
+    rs[5], cs[7] = 0.0, 0.0                                   # an all-zero row and column
+    a, b = a0 * rs[:, None], b0 * cs[None, :]
+    c = gemm.gemm_f32(cuda(a), cuda(b), mode=gemm.F32_F16X2).cpu().numpy()
+    t = _libs.ref_f64(oracle, a, b)
+    scale = rs[:, None].astype(np.float64) * cs[None, :]
+    ok = scale > 0
+    err = np.abs(c - t)[ok] / scale[ok]
+    assert err.max() <= TOL_F16X2 * np.abs(_libs.ref_f64(oracle, a0, b0)).max()
+    assert (c[~ok] == 0).all() and np.isfinite(c).all()
+    ones = torch.ones((300, 300), device="cuda")
+    assert (gemm.gemm_f32(ones * 3, ones, mode=gemm.F32_F16X2) == 900).all()
+
+
 @pytest.mark.parametrize("m,n,k", SHAPES + [(1000, 1100, 4096), (260, 200, 1500)])
 @pytest.mark.parametrize("mode,tol", [("x3", TOL_X3), ("x2", TOL_X2)])
 def test_f32_split_bf16_modes(gemm, oracle, m, n, k, mode, tol):

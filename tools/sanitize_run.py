@@ -8,7 +8,7 @@ dev = "cuda"
 for (m, n, k) in [(256, 256, 128), (300, 392, 96), (128, 256, 64)]:
     A = torch.rand(m, k, device=dev) - 0.5
     B = torch.rand(k, n, device=dev) - 0.5
-    for mode in (0, 1, 2, 3):
+    for mode in (0, 1, 2, 3, 5):
         g.gemm_f32(A, B, mode=mode)
         print(m, n, k, g.last_kernel())
     g.gemm_bf16(A.bfloat16(), B.bfloat16())
