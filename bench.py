@@ -23,6 +23,9 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# stdout must carry exactly one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 N0 = 4096                     # headline size
@@ -248,9 +251,9 @@ def main():
         sampler.start()              # nvidia-smi needs ~0.1 s to start: launch it ahead of the warm-up
     for i in range(max(args.warmup, 3)):
         step(i)
-    barrier()
     if rank == 0:
-        time.sleep(0.15)
+        time.sleep(0.15)             # let the sampler come up; BEFORE the barrier so all ranks start together
+    barrier()
     l0 = g.launch_count()
     g.lib.b200_gemm_debug_kernel_timing(1)      # event pair around every dominant-kernel launch, same stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
