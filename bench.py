@@ -231,7 +231,7 @@ def main():
     rp = None
     if world > 1:
         rowpanel = __import__("importlib").import_module(_libs.PKG + ".rowpanel")
-        rp = rowpanel.RowPanelGemm(lambda a, b, out: g.gemm_f32(a, b, out=out, mode=mode), dist, rank, world,
+        rp = rowpanel.RowPanelGemm(lambda a, b, out, acc: g.gemm_f32(a, b, out=out, mode=mode, accumulate=acc), dist, rank, world,
                                    K, N, BCAST_CHUNKS, dev, torch.float32)
 
     def step(i):
@@ -239,7 +239,7 @@ def main():
         if world == 1:
             g.gemm_f32(A, B, out=Cm, mode=mode)
         else:
-            rp.run(A, B, Cm)        # NCCL broadcast of B (row chunks, in place), then one GEMM on the local row panel
+            rp.run(A, B, Cm)        # NCCL broadcast of B in K-slices (in place) pipelined with C (+)= A[:,ks] * B[ks,:]
 
     def barrier():
         if world > 1:
@@ -313,7 +313,7 @@ def main():
         "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": MODE_DTYPE.get(mode, str(mode)), "data": "synthetic",
         "config": {"workload": f"fp32 SGEMM row-major M={Mloc * world} N=K={N} (BASELINE configs[{1 if args.workload == 'headline' else 4}]); "
-                               f"C row-panel sharded, B broadcast from rank 0 ({BCAST_CHUNKS} row chunks, NCCL) inside every step" if world > 1 else
+                               f"C row-panel sharded, B broadcast from rank 0 inside every step as {BCAST_CHUNKS} K-slices (NCCL, in place) pipelined with the K-sliced GEMM" if world > 1 else
                                f"fp32 SGEMM row-major M=N=K={N0} (BASELINE configs[1], N=4096 point)",
                    "precision_mode": MODE_NAMES.get(mode, str(mode)), "kernel": kernel_name,
                    "l2": f"{R} rotating input/output sets of {3 * N0 * N0 * 4 / 1e6:.0f} MB each (> 126 MB L2 between reuses)",

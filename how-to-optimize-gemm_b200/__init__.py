@@ -22,7 +22,7 @@ OUT_F32, OUT_BF16 = 0, 1
 EXPORTS = [
     "b200_gemm_version", "b200_gemm_device_ok", "b200_gemm_strerror", "b200_gemm_last_kernel",
     "b200_gemm_launch_count", "b200_gemm_default_f32_mode", "b200_gemm_set_default_f32_mode",
-    "b200_gemm_f32", "b200_gemm_f32_host", "b200_gemm_bf16", "b200_gemm_s8s32",
+    "b200_gemm_f32", "b200_gemm_f32_acc", "b200_gemm_f32_host", "b200_gemm_bf16", "b200_gemm_s8s32",
     "b200_gemm_s8s32_host", "b200_convert_f32_to_bf16", "b200_gemm_debug_set_b_desc", "b200_gemm_debug_set_bn",
     "b200_gemm_debug_set_split_chunk", "b200_gemm_debug_kernel_timing", "b200_gemm_debug_kernel_time_ms",
     "b200_gemm_debug_set_cta_group", "b200_gemm_debug_set_split_tail",
@@ -48,6 +48,7 @@ lib.b200_gemm_strerror.argtypes = [_i]
 lib.b200_gemm_last_kernel.restype = C.c_char_p
 lib.b200_gemm_launch_count.restype = C.c_ulonglong
 lib.b200_gemm_f32.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp]
+lib.b200_gemm_f32_acc.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp]
 lib.b200_gemm_f32_host.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i]
 lib.b200_gemm_bf16.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp]
 lib.b200_gemm_s8s32.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]
@@ -117,7 +118,8 @@ def _ld(t):
     return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
 
 
-def gemm_f32(A, B, out=None, mode=F32_AUTO, stream=None):
+def gemm_f32(A, B, out=None, mode=F32_AUTO, stream=None, accumulate=False):
+    """C = A*B, or C += A*B into `out` when accumulate is set (b200_gemm_f32_acc)."""
     import torch
     assert A.dtype == torch.float32 and B.dtype == torch.float32 and A.is_cuda and B.is_cuda
     m, k = A.shape
@@ -125,8 +127,9 @@ def gemm_f32(A, B, out=None, mode=F32_AUTO, stream=None):
     assert k == k2
     if out is None:
         out = torch.empty((m, n), dtype=torch.float32, device=A.device)
-    _check(lib.b200_gemm_f32(m, n, k, A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), out.data_ptr(), _ld(out),
-                             mode, _stream_ptr(stream)))
+    fn = lib.b200_gemm_f32_acc if accumulate else lib.b200_gemm_f32
+    assert not accumulate or out is not None
+    _check(fn(m, n, k, A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), mode, _stream_ptr(stream)))
     return out
 
 

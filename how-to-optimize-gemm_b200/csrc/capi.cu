@@ -181,7 +181,7 @@ template <int KIND, int BN, int STAGES, typename OutT, class Prod = ProdSingle, 
 int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_total, int a_plane_rows,
               const void* B, long long ldb, int b_rows_total, int b_plane_rows, void* C, int ldc,
               cudaStream_t st, const char* name, int chunk_k = 0, const float* row_max = nullptr,
-              const float* col_max = nullptr) {
+              const float* col_max = nullptr, int accumulate = 0) {
   using Cfg = TcConfig<KIND, BN, STAGES, Prod, A_ROW_BYTES, CG>;
   using T = KindTraits<KIND>;
   constexpr CUtensorMapDataType dt = KIND == KIND_F16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
@@ -208,6 +208,7 @@ int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_tota
   if (p.chunk_kb < 1) p.chunk_kb = 1;
   p.dbg_b_lbo = g_dbg_b_lbo; p.dbg_b_sbo = g_dbg_b_sbo;
   p.row_max = row_max; p.col_max = col_max;
+  p.accumulate = accumulate;
   auto kern = gemm_tc_kernel<KIND, BN, STAGES, OutT, Prod, A_ROW_BYTES, CG>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -305,8 +306,14 @@ bool use_pair(int m, int n) {
     default:  return launch_tc<KIND, 128, 6, OUT>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, NAME "_128x128"); \
   }
 
-int tc_tf32(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C, int ldc, cudaStream_t st) {
-  TC_PLAIN(KIND_TF32, float, "tc_tf32")
+int tc_tf32(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C, int ldc, cudaStream_t st, int acc = 0) {
+  if (use_pair(m, n))
+    return launch_tc<KIND_TF32, 256, 6, float, ProdSingle, 128, 2>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_tf32_2cta_256x256", 0, nullptr, nullptr, acc);
+  switch (pick_bn(m, n, true)) {
+    case 256: return launch_tc<KIND_TF32, 256, 4, float>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_tf32_128x256", 0, nullptr, nullptr, acc);
+    case 192: return launch_tc<KIND_TF32, 192, 5, float>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_tf32_128x192", 0, nullptr, nullptr, acc);
+    default:  return launch_tc<KIND_TF32, 128, 6, float>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_tf32_128x128", 0, nullptr, nullptr, acc);
+  }
 }
 int tc_bf16_f32(int m, int n, int k, const void* A, int lda, const void* B, int ldb, void* C, int ldc, cudaStream_t st) {
   TC_PLAIN(KIND_F16, float, "tc_bf16")
@@ -333,7 +340,7 @@ SplitWs g_split_ws;
 
 template <int NP>
 int gemm_f32_split(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                   cudaStream_t st) {
+                   cudaStream_t st, int acc = 0) {
   const long long pka = ((long long)k + 7) & ~7LL;          // A plane pitch (elements), 16-byte multiple
   const long long pnb = ((long long)n + 7) & ~7LL;          // B plane pitch
   const int kp = (k + 31) & ~31;                            // B plane height: zero rows pad K to the k-block
@@ -359,21 +366,21 @@ int gemm_f32_split(int m, int n, int k, const float* A, int lda, const float* B,
   if (rc) return rc;
   if (use_pair(m, n)) {
     if constexpr (NP == 3)
-      return launch_tc<KIND_F16, 256, 4, float, ProdX3, 64, 2>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x3_2cta_256x256", g_split_chunk_k[0]);
+      return launch_tc<KIND_F16, 256, 4, float, ProdX3, 64, 2>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x3_2cta_256x256", g_split_chunk_k[0], nullptr, nullptr, acc);
     else
-      return launch_tc<KIND_F16, 256, 6, float, ProdX2, 64, 2>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x2_2cta_256x256", g_split_chunk_k[1]);
+      return launch_tc<KIND_F16, 256, 6, float, ProdX2, 64, 2>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x2_2cta_256x256", g_split_chunk_k[1], nullptr, nullptr, acc);
   }
   const int bn = pick_bn(m, n, NP == 2);
   if constexpr (NP == 3) {
     if (bn == 192)
-      return launch_tc<KIND_F16, 192, 3, float, ProdX3, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x3_128x192", g_split_chunk_k[0]);
-    return launch_tc<KIND_F16, 128, 4, float, ProdX3, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x3_128x128", g_split_chunk_k[0]);
+      return launch_tc<KIND_F16, 192, 3, float, ProdX3, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x3_128x192", g_split_chunk_k[0], nullptr, nullptr, acc);
+    return launch_tc<KIND_F16, 128, 4, float, ProdX3, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x3_128x128", g_split_chunk_k[0], nullptr, nullptr, acc);
   } else {
     if (bn == 256)
-      return launch_tc<KIND_F16, 256, 4, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x2_128x256", g_split_chunk_k[1]);
+      return launch_tc<KIND_F16, 256, 4, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x2_128x256", g_split_chunk_k[1], nullptr, nullptr, acc);
     if (bn == 192)
-      return launch_tc<KIND_F16, 192, 5, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x2_128x192", g_split_chunk_k[1]);
-    return launch_tc<KIND_F16, 128, 6, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x2_128x128", g_split_chunk_k[1]);
+      return launch_tc<KIND_F16, 192, 5, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x2_128x192", g_split_chunk_k[1], nullptr, nullptr, acc);
+    return launch_tc<KIND_F16, 128, 6, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x2_128x128", g_split_chunk_k[1], nullptr, nullptr, acc);
   }
 }
 
@@ -381,7 +388,7 @@ int gemm_f32_split(int m, int n, int k, const float* A, int lda, const float* B,
 // power-of-two scalings that bring every operand into [-1, 1] (fp16 has 5 exponent bits); the
 // epilogue multiplies them back.  Launches: memset, 2 x absmax, 2 x split, GEMM.
 int gemm_f32_split_f16(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                       cudaStream_t st) {
+                       cudaStream_t st, int acc = 0) {
   constexpr int NP = 2;
   const long long pka = ((long long)k + 7) & ~7LL, pnb = ((long long)n + 7) & ~7LL;
   const int kp = (k + 31) & ~31;
@@ -417,12 +424,12 @@ int gemm_f32_split_f16(int m, int n, int k, const float* A, int lda, const float
   if (rc) return rc;
   if (use_pair(m, n))
     return launch_tc<KIND_FP16, 256, 6, float, ProdX2, 64, 2>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st,
-                                                              "tc_f16x2_2cta_256x256", g_split_chunk_k[1], rmax, cmax);
+                                                              "tc_f16x2_2cta_256x256", g_split_chunk_k[1], rmax, cmax, acc);
   if (pick_bn(m, n, true, false) == 256)
     return launch_tc<KIND_FP16, 256, 4, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st,
-                                                           "tc_f16x2_128x256", g_split_chunk_k[1], rmax, cmax);
+                                                           "tc_f16x2_128x256", g_split_chunk_k[1], rmax, cmax, acc);
   return launch_tc<KIND_FP16, 128, 6, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st,
-                                                         "tc_f16x2_128x128", g_split_chunk_k[1], rmax, cmax);
+                                                         "tc_f16x2_128x128", g_split_chunk_k[1], rmax, cmax, acc);
 }
 
 int launch_ffma(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
@@ -498,18 +505,14 @@ int gemm_f32_impl(int m, int n, int k, const float* dA, int lda, const float* dB
       if (tma) return launch_ffma(m, n, k, dA, lda, dB, ldb, dC, ldc, accumulate, st);
       return launch_generic<float, float>(m, n, k, dA, lda, dB, ldb, dC, ldc, accumulate, st, "generic_f32_64x64");
     case B200_F32_TF32:
-      if (accumulate) return B200_ERR_UNSUPPORTED;
-      if (!tma) return launch_generic<float, float>(m, n, k, dA, lda, dB, ldb, dC, ldc, 0, st, "generic_f32_64x64");
-      return tc_tf32(m, n, k, dA, lda, dB, ldb, dC, ldc, st);
+      if (!tma) return launch_generic<float, float>(m, n, k, dA, lda, dB, ldb, dC, ldc, accumulate, st, "generic_f32_64x64");
+      return tc_tf32(m, n, k, dA, lda, dB, ldb, dC, ldc, st, accumulate);
     case B200_F32_BF16X3:
-      if (accumulate) return B200_ERR_UNSUPPORTED;
-      return gemm_f32_split<3>(m, n, k, dA, lda, dB, ldb, dC, ldc, st);
+      return gemm_f32_split<3>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, accumulate);
     case B200_F32_BF16X2:
-      if (accumulate) return B200_ERR_UNSUPPORTED;
-      return gemm_f32_split<2>(m, n, k, dA, lda, dB, ldb, dC, ldc, st);
+      return gemm_f32_split<2>(m, n, k, dA, lda, dB, ldb, dC, ldc, st, accumulate);
     case B200_F32_F16X2:
-      if (accumulate) return B200_ERR_UNSUPPORTED;
-      return gemm_f32_split_f16(m, n, k, dA, lda, dB, ldb, dC, ldc, st);
+      return gemm_f32_split_f16(m, n, k, dA, lda, dB, ldb, dC, ldc, st, accumulate);
     default:
       return B200_ERR_UNSUPPORTED;
   }
@@ -565,6 +568,11 @@ int b200_gemm_debug_kernel_time_ms(double* sum_ms) {
 int b200_gemm_f32(int m, int n, int k, const float* dA, int lda, const float* dB, int ldb, float* dC,
                   int ldc, int precision_mode, void* stream) {
   return gemm_f32_impl(m, n, k, dA, lda, dB, ldb, dC, ldc, precision_mode, 0, (cudaStream_t)stream);
+}
+
+int b200_gemm_f32_acc(int m, int n, int k, const float* dA, int lda, const float* dB, int ldb, float* dC,
+                      int ldc, int precision_mode, void* stream) {
+  return gemm_f32_impl(m, n, k, dA, lda, dB, ldb, dC, ldc, precision_mode, 1, (cudaStream_t)stream);
 }
 
 int b200_gemm_bf16(int m, int n, int k, const uint16_t* dA, int lda, const uint16_t* dB, int ldb,
@@ -646,7 +654,7 @@ int b200_gemm_f32_host(int m, int n, int k, const float* A, int lda, const float
   rc = ensure_device();
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(g_host_mu);
-  float *dA = nullptr, *dB = nullptr, *dC = nullptr, *dT = nullptr;
+  float *dA = nullptr, *dB = nullptr, *dC = nullptr;
   const int mode = resolve_f32_mode(precision_mode);
   // device images: pitches rounded up to 4 floats so the TMA paths apply to any k, n
   const int pk = (k + 3) & ~3, pn = (n + 3) & ~3;
@@ -660,19 +668,8 @@ int b200_gemm_f32_host(int m, int n, int k, const float* A, int lda, const float
   }
   CK(scratch(2, pc * m, (void**)&dC));
   CK(cudaMemcpy2DAsync(dC, pc, C, (size_t)ldc * 4, (size_t)n * 4, m, cudaMemcpyHostToDevice, st));
-  if (mode == B200_F32_STRICT) {
-    rc = gemm_f32_impl(m, n, k, dA, pk, dB, pn, dC, pn, mode, /*accumulate=*/1, st);
-    if (rc) return rc;
-  } else {
-    CK(scratch(3, pc * m, (void**)&dT));
-    rc = gemm_f32_impl(m, n, k, dA, pk, dB, pn, dT, pn, mode, 0, st);
-    if (rc) return rc;
-    dim3 grid((n + 255) / 256, m < 4096 ? m : 4096);
-    add_inplace_kernel<float><<<grid, 256, 0, st>>>(m, n, dC, pn, dT, pn);
-    g_launches++;
-    rc = last_launch_status();
-    if (rc) return rc;
-  }
+  rc = gemm_f32_impl(m, n, k, dA, pk, dB, pn, dC, pn, mode, /*accumulate=*/1, st);   // C += A*B on the device
+  if (rc) return rc;
   CK(cudaMemcpy2DAsync(C, (size_t)ldc * 4, dC, pc, (size_t)n * 4, m, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return 0;

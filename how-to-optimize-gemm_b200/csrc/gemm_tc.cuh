@@ -82,6 +82,7 @@ struct TcParams {
   // fp16 split; the epilogue multiplies back by 2^e(row) * 2^e(col), exact.  Null = no scaling.
   const float* row_max;    // [M] max |A(i,:)|
   const float* col_max;    // [N] max |B(:,j)|
+  int accumulate;          // 1: C += A*B (every partial, including the first, is folded into C); fp32/int32 only
   int dbg_b_lbo, dbg_b_sbo;  // 0 = defaults (probe hook, see b200_gemm_debug_set_b_desc)
 };
 
@@ -373,7 +374,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
      // accumulator with truncation, so a long K chain drifts (measured: error grows ~K).  Each
      // K-chunk gets a fresh TMEM accumulator and is folded into C here with a rounded fp32 add.
      for (int c0 = it.kb0; c0 < it.kb1; c0 += p.chunk_kb) {
-      const bool fold = c0 != it.kb0 || it.part > 0;
+      const bool fold = p.accumulate != 0 || c0 != it.kb0 || it.part > 0;
       mbar_wait(bar_tfull + 8 * as, aph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::ACC_STRIDE;

@@ -96,6 +96,14 @@ int b200_gemm_f32(int m, int n, int k,
                   const float* dA, int lda, const float* dB, int ldb,
                   float* dC, int ldc, int precision_mode, void* stream);
 
+/* fp32: C += A*B on DEVICE pointers — the CPU harnesses' contract (aarch64/MMult0.cpp:16) without
+ * the staging copies; also what lets a K-sliced operand stream (B arriving in row chunks over
+ * NVLink) be consumed chunk by chunk.  STRICT keeps one fused chain per element starting from C(i,j);
+ * the tensor-core modes fold their fp32 partial sums into C with rounded adds. */
+int b200_gemm_f32_acc(int m, int n, int k,
+                      const float* dA, int lda, const float* dB, int ldb,
+                      float* dC, int ldc, int precision_mode, void* stream);
+
 /* fp32 with HOST pointers and the CPU harness contract C += A*B
  * (aarch64/MMult0.cpp:11-19; harness zeroes C first, aarch64/test_MMult.cpp:107).
  * Stages H2D, runs b200_gemm_f32 on the device, adds into C on the device,

@@ -213,6 +213,34 @@ def test_golden_s8(gemm, idx):
     assert np.array_equal(c, cref)          # host entry = what aarch64-int8/test_MMult.c:98 calls
 
 
+@pytest.mark.parametrize("mode,tol", [("strict", 0.0), ("tf32", TOL_TF32), ("x3", TOL_X3), ("x2", TOL_X2), ("f16x2", TOL_F16X2)])
+@pytest.mark.parametrize("m,n,k", [(300, 520, 200), (512, 768, 1536), (77, 96, 80)])
+def test_f32_accumulate_entry(gemm, oracle, m, n, k, mode, tol):
+    """b200_gemm_f32_acc: C += A*B on device pointers, and K-sliced accumulation (what the multi-GPU
+    row-panel pipeline does with B arriving in row chunks) equals the one-shot product."""
+    md = {"strict": gemm.F32_STRICT, "tf32": gemm.F32_TF32, "x3": gemm.F32_BF16X3, "x2": gemm.F32_BF16X2,
+          "f16x2": gemm.F32_F16X2}[mode]
+    a, b, c0 = _libs.gen_f32(oracle, m, k, 41), _libs.gen_f32(oracle, k, n, 42), _libs.gen_f32(oracle, m, n, 43)
+    A, B = cuda(a), cuda(b)
+    C = cuda(c0)
+    gemm.gemm_f32(A, B, out=C, mode=md, accumulate=True)
+    t = _libs.ref_f64(oracle, a, b) + c0
+    if mode == "strict":
+        assert np.array_equal(C.cpu().numpy(), _libs.ref_f32_fma(oracle, a, b, c0))     # chain continues from C
+    else:
+        assert rel(C.cpu().numpy(), t) <= tol
+    # K-sliced: C = A[:, :k1]*B[:k1] ; C += A[:, k1:]*B[k1:]   (strided A views, contiguous B row blocks)
+    k1 = (k // 2 + 7) // 8 * 8
+    C2 = torch.empty((m, n), device="cuda")
+    gemm.gemm_f32(A[:, :k1], B[:k1], out=C2, mode=md)
+    gemm.gemm_f32(A[:, k1:], B[k1:], out=C2, mode=md, accumulate=True)
+    t2 = _libs.ref_f64(oracle, a, b)
+    if mode == "strict":
+        assert np.array_equal(C2.cpu().numpy(), _libs.ref_f32_fma(oracle, a, b))         # same chain, cut in two launches
+    else:
+        assert rel(C2.cpu().numpy(), t2) <= tol
+
+
 # ---- host entry points: the CPU harness contract C += A*B ----------------------------------------
 def test_host_entry_accumulates(gemm, oracle):
     m, n, k = 96, 80, 160

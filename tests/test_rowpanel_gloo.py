@@ -34,8 +34,9 @@ def _worker(rank, world, port, M, N, K, panel, out_dir):
     o = L.load_oracle()
     o.oracle_set_threads(1)
 
-    def host_gemm(a, b, out):
-        c = L.ref_f32_fma(o, np.ascontiguousarray(a.numpy()), np.ascontiguousarray(b.numpy()))
+    def host_gemm(a, b, out, accumulate):
+        c0 = np.ascontiguousarray(out.numpy()) if accumulate else None     # C += A*B: chain continues from C
+        c = L.ref_f32_fma(o, np.ascontiguousarray(a.numpy()), np.ascontiguousarray(b.numpy()), c0)
         out.copy_(torch.from_numpy(c))
 
     A = torch.from_numpy(L.gen_f32(o, M, K, 100))

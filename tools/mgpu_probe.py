@@ -25,6 +25,7 @@ for mode in (2, 1):
     timeit(f"gemm only mode {mode}", lambda: g.gemm_f32(A, B, out=C, mode=mode))
     timeit("broadcast only", lambda: dist.broadcast(B, src=0))
     timeit(f"broadcast + gemm same stream mode {mode}", lambda: (dist.broadcast(B, src=0), g.gemm_f32(A, B, out=C, mode=mode)))
-    rp = rowpanel.RowPanelGemm(lambda a, b, out: g.gemm_f32(a, b, out=out, mode=mode), dist, rank, world, N, N, 4, dev, torch.float32)
-    timeit(f"RowPanelGemm.run mode {mode}", lambda: rp.run(A, B, C))
+    for chunks, pipe in ((4, False), (2, True), (4, True), (8, True)):
+        rp = rowpanel.RowPanelGemm(lambda a, b, out, acc: g.gemm_f32(a, b, out=out, mode=mode, accumulate=acc), dist, rank, world, N, N, chunks, dev, torch.float32, pipeline=pipe)
+        timeit(f"RowPanelGemm.run mode {mode} chunks {chunks} pipeline {pipe}", lambda: rp.run(A, B, C))
 dist.barrier(); dist.destroy_process_group()
