@@ -385,21 +385,24 @@ def main():
         if "strict_ffma" in modes:
             modes["strict_ffma"]["frac_of_fp32_cuda_core_peak"] = modes["strict_ffma"]["gflops"] / 1e3 / fp32_peak
         # ---- GFLOP/s-vs-N curve in the reference's output_*.m format ------------------------------
-        sweep = []
+        sweep, sweep_kernels = [], []
+        sweep_mode = args.mode if args.mode >= 0 else g.F32_AUTO    # the library default, size heuristic included
         for n in range(256, 4097, 256):
             a = torch.rand((n, n), device=dev) * 2 - 1
             b = torch.rand((n, n), device=dev) * 2 - 1
             c = torch.empty((n, n), device=dev)
             for _ in range(3):
-                g.gemm_f32(a, b, out=c, mode=mode)
+                g.gemm_f32(a, b, out=c, mode=sweep_mode)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             for _ in range(20):            # NREPEATS = 20 back-to-back launches (cuda/parameters.h:24)
-                g.gemm_f32(a, b, out=c, mode=mode)
+                g.gemm_f32(a, b, out=c, mode=sweep_mode)
             e.record()
             torch.cuda.synchronize()
             sweep.append([n, round(2.0 * n ** 3 / (s.elapsed_time(e) / 20) / 1e6, 2)])
+            sweep_kernels.append(g.last_kernel())
         out["sweep"] = sweep
+        out["sweep_kernels"] = sweep_kernels       # AUTO takes the single-launch strict kernel below ~1024^3
         out["cpu_baseline"] = cpu_baseline(o)
     _phase("extras done")
     print(json.dumps(out))

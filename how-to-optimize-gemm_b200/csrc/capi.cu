@@ -646,6 +646,28 @@ cudaError_t scratch(int i, size_t bytes, void** out) {
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cudaGetLastError(); return (int)e_; } } while (0)
 
+// Streams / events of the pipelined host path (created once).
+namespace {
+struct HostPipe {
+  bool ready = false;
+  cudaStream_t h2d = nullptr, comp = nullptr, d2h = nullptr;
+  cudaEvent_t in[8] = {}, done[8] = {};
+  cudaError_t init() {
+    if (ready) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    for (int i = 0; i < 8; i++) {
+      if ((e = cudaEventCreateWithFlags(&in[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+      if ((e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    ready = true;
+    return cudaSuccess;
+  }
+} g_pipe;
+}  // namespace
+
 int b200_gemm_f32_host(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C,
                        int ldc, int precision_mode) {
   int rc = check_args(m, n, k, A, lda, B, ldb, C, ldc);
@@ -659,19 +681,48 @@ int b200_gemm_f32_host(int m, int n, int k, const float* A, int lda, const float
   // device images: pitches rounded up to 4 floats so the TMA paths apply to any k, n
   const int pk = (k + 3) & ~3, pn = (n + 3) & ~3;
   const size_t pa = (size_t)pk * 4, pb = (size_t)pn * 4, pc = (size_t)pn * 4;
-  cudaStream_t st = 0;
   if (k > 0) {
     CK(scratch(0, pa * m, (void**)&dA));
     CK(scratch(1, pb * k, (void**)&dB));
-    CK(cudaMemcpy2DAsync(dA, pa, A, (size_t)lda * 4, (size_t)k * 4, m, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpy2DAsync(dB, pb, B, (size_t)ldb * 4, (size_t)n * 4, k, cudaMemcpyHostToDevice, st));
   }
   CK(scratch(2, pc * m, (void**)&dC));
-  CK(cudaMemcpy2DAsync(dC, pc, C, (size_t)ldc * 4, (size_t)n * 4, m, cudaMemcpyHostToDevice, st));
-  rc = gemm_f32_impl(m, n, k, dA, pk, dB, pn, dC, pn, mode, /*accumulate=*/1, st);   // C += A*B on the device
-  if (rc) return rc;
-  CK(cudaMemcpy2DAsync(C, (size_t)ldc * 4, dC, pc, (size_t)n * 4, m, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  // Large problems: row-block pipeline over three streams, so the D2H of C block i overlaps the H2D
+  // of block i+1 (PCIe is full duplex) and the GEMMs hide under the copies.  The path is copy-bound:
+  // 268 MB cross the bus per 4096^3 call against 0.6 ms of math.
+  const int blocks = (k > 0 && m >= 2048 && (double)m * n * k >= 8.0e9) ? 4 : 1;
+  if (blocks == 1) {
+    cudaStream_t st = 0;
+    if (k > 0) {
+      CK(cudaMemcpy2DAsync(dA, pa, A, (size_t)lda * 4, (size_t)k * 4, m, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpy2DAsync(dB, pb, B, (size_t)ldb * 4, (size_t)n * 4, k, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpy2DAsync(dC, pc, C, (size_t)ldc * 4, (size_t)n * 4, m, cudaMemcpyHostToDevice, st));
+    rc = gemm_f32_impl(m, n, k, dA, pk, dB, pn, dC, pn, mode, /*accumulate=*/1, st);   // C += A*B on the device
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(C, (size_t)ldc * 4, dC, pc, (size_t)n * 4, m, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+  }
+  CK(g_pipe.init());
+  CK(cudaMemcpy2DAsync(dB, pb, B, (size_t)ldb * 4, (size_t)n * 4, k, cudaMemcpyHostToDevice, g_pipe.h2d));
+  const int rows_per = ((m + blocks - 1) / blocks + 255) & ~255;       // whole 256-row pair tiles per block
+  int nb = 0;
+  for (int r0 = 0; r0 < m; r0 += rows_per, nb++) {
+    const int rows = m - r0 < rows_per ? m - r0 : rows_per;
+    float* dAi = dA + (size_t)r0 * pk;
+    float* dCi = dC + (size_t)r0 * pn;
+    CK(cudaMemcpy2DAsync(dAi, pa, A + (size_t)r0 * lda, (size_t)lda * 4, (size_t)k * 4, rows, cudaMemcpyHostToDevice, g_pipe.h2d));
+    CK(cudaMemcpy2DAsync(dCi, pc, C + (size_t)r0 * ldc, (size_t)ldc * 4, (size_t)n * 4, rows, cudaMemcpyHostToDevice, g_pipe.h2d));
+    CK(cudaEventRecord(g_pipe.in[nb], g_pipe.h2d));
+    CK(cudaStreamWaitEvent(g_pipe.comp, g_pipe.in[nb], 0));
+    rc = gemm_f32_impl(rows, n, k, dAi, pk, dB, pn, dCi, pn, mode, /*accumulate=*/1, g_pipe.comp);
+    if (rc) return rc;
+    CK(cudaEventRecord(g_pipe.done[nb], g_pipe.comp));
+    CK(cudaStreamWaitEvent(g_pipe.d2h, g_pipe.done[nb], 0));
+    CK(cudaMemcpy2DAsync(C + (size_t)r0 * ldc, (size_t)ldc * 4, dCi, pc, (size_t)n * 4, rows, cudaMemcpyDeviceToHost, g_pipe.d2h));
+  }
+  CK(cudaStreamSynchronize(g_pipe.d2h));
+  CK(cudaStreamSynchronize(g_pipe.comp));
   return 0;
 }
 

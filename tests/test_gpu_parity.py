@@ -254,6 +254,19 @@ def test_host_entry_accumulates(gemm, oracle):
     assert rel(c, t) <= TOL_TF32
 
 
+def test_host_entry_pipelined_large(gemm, oracle):
+    """Above ~8 GFLOP the host entry runs a row-block pipeline over three streams (H2D / GEMM / D2H):
+    same contract, and strict stays bit-exact because every row block is the same per-element chain."""
+    m, n, k = 2304, 1024, 4096          # blocks of 768 -> rounded to 768? (whole pair tiles): ragged last block
+    a, b, c0 = _libs.gen_f32(oracle, m, k, 51), _libs.gen_f32(oracle, k, n, 52), _libs.gen_f32(oracle, m, n, 53)
+    c = c0.copy()
+    gemm.MY_MMult(m, n, k, a, k, b, n, c, n, mode=gemm.F32_STRICT)
+    assert np.array_equal(c, _libs.ref_f32_fma(oracle, a, b, c0))
+    c = c0.copy()
+    gemm.MY_MMult(m, n, k, a, k, b, n, c, n, mode=gemm.F32_BF16X3)
+    assert rel(c, _libs.ref_f64(oracle, a, b) + c0) <= TOL_X3
+
+
 # ---- BASELINE.json full sizes: size-independent properties ---------------------------------------
 @pytest.mark.parametrize("N", [4096])
 def test_full_size_properties_f32(gemm, oracle, N):
