@@ -175,6 +175,7 @@ int launch_generic(int m, int n, int k, const InT* A, int lda, const InT* B, int
 int g_force_bn = 0;          // test/tuning hook (b200_gemm_debug_set_bn): 0 = heuristic
 int g_group_rows = 0;         // tuning hook: rows per raster group of the tensor-core kernels (0 = 2048)
 int g_force_cg = 0;
+int g_ffma_fat = -1;        // strict kernel: 1 = 128x256 fat-thread variant, 0 = 128x128, -1 = by size
 int g_ffma_halves = 1;      // strict kernel: split the tail round into half tiles (tuning hook)          // test/tuning hook (b200_gemm_debug_set_cta_group): 0 = auto, 1, 2
 
 template <int KIND, int BN, int STAGES, typename OutT, class Prod = ProdSingle, int A_ROW_BYTES = 128, int CG = 1>
@@ -467,6 +468,41 @@ int launch_ffma(int m, int n, int k, const float* A, int lda, const float* B, in
   return last_launch_status();
 }
 
+int launch_ffma_fat(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                int accumulate, cudaStream_t st) {
+  using Cfg = FfmaFatCfg;
+  CUtensorMap tmA, tmB;
+  int rc = get_map(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, k, m, (unsigned long long)lda * 4, Cfg::BK, Cfg::BM, 1);
+  if (rc) return rc;
+  rc = get_map(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, n, k, (unsigned long long)ldb * 4, Cfg::BN, Cfg::BK, 0);
+  if (rc) return rc;
+  FfmaParams p;
+  p.C = C; p.ldc = ldc; p.M = m; p.N = n; p.K = k;
+  p.vec_ok = aligned16(C) && (ldc % 4) == 0;
+  p.accumulate = accumulate;
+  p.tiles_m = (m + Cfg::BM - 1) / Cfg::BM;
+  p.tiles_n = (n + Cfg::BN - 1) / Cfg::BN;
+  p.group_m = 8;
+  // 1 CTA per SM: tiles of the last, at most half-full round are issued as two half tiles each
+  const int tiles = p.tiles_m * p.tiles_n, slots = g_dev.sms;
+  const int rem = tiles % slots;
+  const bool halves = g_ffma_halves && rem > 0 && 2 * rem <= slots;
+  p.full_tiles = halves ? tiles - rem : tiles;
+  const int ctas = p.full_tiles + 2 * (tiles - p.full_tiles);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_ffma_fat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    attr_set = true;
+  }
+  g_ktimer.begin(st);
+  gemm_ffma_fat_kernel<<<ctas, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  g_ktimer.end(st);
+  g_launches++;
+  t_last_kernel = "ffma_fat_128x256x32_tma";
+  return last_launch_status();
+}
+
 bool tma_ok(const void* A, int lda, const void* B, int ldb, int elem) {
   return aligned16(A) && aligned16(B) && ((long long)lda * elem) % 16 == 0 && ((long long)ldb * elem) % 16 == 0;
 }
@@ -502,6 +538,10 @@ int gemm_f32_impl(int m, int n, int k, const float* dA, int lda, const float* dB
   if (was_auto && mode == B200_F32_BF16X3 && tma && (double)m * n * k <= 1.1e9) mode = B200_F32_STRICT;
   switch (mode) {
     case B200_F32_STRICT:
+      // 128x256 fat-thread tiles once they fill most of the machine (measured at N = 4096 / 3072 / 2048:
+      // 58.9 / 57.7 / 50.8 TFLOP/s against 58.5 / 57.2 / 49.3 for 128x128; at 1024 the small tile wins 40.6 : 24.1)
+      if (tma && (g_ffma_fat == 1 || (g_ffma_fat < 0 && (long long)((m + 127) / 128) * ((n + 255) / 256) >= 96)))
+        return launch_ffma_fat(m, n, k, dA, lda, dB, ldb, dC, ldc, accumulate, st);
       if (tma) return launch_ffma(m, n, k, dA, lda, dB, ldb, dC, ldc, accumulate, st);
       return launch_generic<float, float>(m, n, k, dA, lda, dB, ldb, dC, ldc, accumulate, st, "generic_f32_64x64");
     case B200_F32_TF32:
@@ -548,7 +588,7 @@ void b200_gemm_debug_set_bn(int bn) { g_force_bn = bn; }
 void b200_gemm_debug_set_cta_group(int cg) { g_force_cg = cg; }
 void b200_gemm_debug_set_split_tail(int on) { g_split_tail = on; }
 void b200_gemm_debug_set_group_rows(int rows) { g_group_rows = rows; }
-void b200_gemm_debug_set_ffma_variant(int v) { g_ffma_halves = v; }
+void b200_gemm_debug_set_ffma_variant(int v) { g_ffma_halves = v & 1; g_ffma_fat = v < 0 ? -1 : (v >> 1) & 1; }
 void b200_gemm_debug_set_split_chunk(int x3_k, int x2_k) { g_split_chunk_k[0] = x3_k; g_split_chunk_k[1] = x2_k; }
 void b200_gemm_debug_kernel_timing(int enable) { g_ktimer.on = enable != 0; g_ktimer.n = 0; }
 int b200_gemm_debug_kernel_time_ms(double* sum_ms) {

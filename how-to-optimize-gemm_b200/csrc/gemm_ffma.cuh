@@ -209,4 +209,174 @@ gemm_ffma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   else       ffma_tile<4>(tmA, tmB, p, m0, n0, i0, sA, sB, bar_full, bar_empty);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// "Fat-thread" variant: 128 x 256 CTA tile, 256 threads, 8 x 16 outputs per thread (128 accumulators,
+// 1 CTA per SM, up to 255 registers).  Same arithmetic contract.  The larger register budget allows
+// what the 128-register 8x8 kernel cannot: both operand streams are fetched one step ahead (A for the
+// next 4 k-steps, B for the next k-step) while the current 64 FFMA2 issue, so no shared-memory latency
+// is exposed at k-chunk boundaries, and each k-step needs 6 LDS.128 per 64 FFMA2 instead of 4 per 32.
+struct FfmaFatCfg {
+  static constexpr int BM = 128, BN = 256, BK = 32, STAGES = 3;
+  static constexpr int A_STAGE = BM * BK * 4;     // 16 KB, swizzled 128 B rows
+  static constexpr int B_STAGE = BK * BN * 4;     // 32 KB, 32 rows x 1024 B
+  static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * STAGES * 8;
+  static constexpr int THREADS = 256;
+};
+
+template <int NI>
+__device__ __forceinline__ void ffma_fat_tile(const CUtensorMap& tmA, const CUtensorMap& tmB, const FfmaParams& p,
+                                              int m0, int n0, int i0, uint32_t sA, uint32_t sB,
+                                              uint32_t bar_full, uint32_t bar_empty) {
+  using Cfg = FfmaFatCfg;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ty = (warp >> 1) * 4 + (lane >> 3);   // 0..15 : rows ty + 16*i
+  const int tx = (warp & 1) * 8 + (lane & 7);     // 0..15 : columns tx*4 + 64*j, j = 0..3
+  const int num_kb = (p.K + Cfg::BK - 1) / Cfg::BK;
+
+  auto issue = [&](int kb) {
+    const int s = kb % Cfg::STAGES;
+    const uint32_t full = bar_full + 8 * s;
+    mbar_arrive_expect_tx(full, Cfg::STAGE_BYTES);
+    tma_load_2d(sA + s * Cfg::A_STAGE, &tmA, full, kb * Cfg::BK, m0);
+    tma_load_2d(sB + s * Cfg::B_STAGE, &tmB, full, n0, kb * Cfg::BK);
+  };
+  if (threadIdx.x == 0) {
+    for (int kb = 0; kb < Cfg::STAGES - 1 && kb < num_kb; kb++) issue(kb);
+  }
+
+  float2 acc[NI][8];
+#pragma unroll
+  for (int i = 0; i < NI; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[i][j] = make_float2(0.0f, 0.0f);
+  if (p.accumulate) {
+#pragma unroll
+    for (int i = 0; i < NI; i++)
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const int gm = m0 + ty + 16 * (i0 + i), gn = n0 + tx * 4 + 64 * (j >> 2) + (j & 3);
+        if (gm < p.M && gn < p.N) {
+          const float v = p.C[(long long)gm * p.ldc + gn];
+          if (j & 1) acc[i][j >> 1].y = v; else acc[i][j >> 1].x = v;
+        }
+      }
+  }
+  const uint32_t a_thr = sA + (ty + 16 * i0) * 128;
+  const uint32_t a_swz16 = (ty & 7) << 4;
+  const uint32_t b_thr = sB + tx * 16;
+
+  for (int kb = 0; kb < num_kb; kb++) {
+    const int s = kb % Cfg::STAGES;
+    const uint32_t use = kb / Cfg::STAGES;
+    if (threadIdx.x == 0) {
+      const int nk = kb + Cfg::STAGES - 1;
+      if (nk < num_kb) {
+        if (kb >= 1) mbar_wait(bar_empty + 8 * (nk % Cfg::STAGES), ((nk / Cfg::STAGES) - 1) & 1);
+        issue(nk);
+      }
+    }
+    mbar_wait(bar_full + 8 * s, use & 1);
+    const uint32_t a_st = a_thr + s * Cfg::A_STAGE;
+    const uint32_t b_st = b_thr + s * Cfg::B_STAGE;
+    float4 a4[2][NI];
+    float4 bq[2][4];
+#pragma unroll
+    for (int i = 0; i < NI; i++) a4[0][i] = lds128(a_st + a_swz16 + i * (16 * 128));
+#pragma unroll
+    for (int j = 0; j < 4; j++) bq[0][j] = lds128(b_st + j * 256);
+#pragma unroll
+    for (int kc = 0; kc < Cfg::BK / 4; kc++) {
+      const int ac = kc & 1;
+      if (kc + 1 < Cfg::BK / 4) {
+#pragma unroll
+        for (int i = 0; i < NI; i++)
+          a4[ac ^ 1][i] = lds128(a_st + (((uint32_t)(kc + 1) << 4) ^ a_swz16) + i * (16 * 128));
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        const int k = kc * 4 + kk;
+        if (k + 1 < Cfg::BK) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) bq[(k + 1) & 1][j] = lds128(b_st + (k + 1) * 1024 + j * 256);
+        }
+        float2 bv[8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          bv[2 * j] = make_float2(bq[k & 1][j].x, bq[k & 1][j].y);
+          bv[2 * j + 1] = make_float2(bq[k & 1][j].z, bq[k & 1][j].w);
+        }
+#pragma unroll
+        for (int i = 0; i < NI; i++) {
+          const float av = kk == 0 ? a4[ac][i].x : kk == 1 ? a4[ac][i].y : kk == 2 ? a4[ac][i].z : a4[ac][i].w;
+          const float2 aa = make_float2(av, av);
+#pragma unroll
+          for (int j = 0; j < 8; j++) acc[i][j] = __ffma2_rn(aa, bv[j], acc[i][j]);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+  }
+
+#pragma unroll
+  for (int i = 0; i < NI; i++) {
+    const int gm = m0 + ty + 16 * (i0 + i);
+    if (gm >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int gn = n0 + tx * 4 + 64 * j;
+      float* dst = p.C + (long long)gm * p.ldc + gn;
+      if (p.vec_ok && gn + 4 <= p.N) {
+        *reinterpret_cast<float4*>(dst) =
+            make_float4(acc[i][2 * j].x, acc[i][2 * j].y, acc[i][2 * j + 1].x, acc[i][2 * j + 1].y);
+      } else {
+        const float ev[4] = {acc[i][2 * j].x, acc[i][2 * j].y, acc[i][2 * j + 1].x, acc[i][2 * j + 1].y};
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+          if (gn + e < p.N) dst[e] = ev[e];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+gemm_ffma_fat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const FfmaParams p) {
+  using Cfg = FfmaFatCfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + Cfg::STAGES * Cfg::A_STAGE;
+  const uint32_t bar_full = sB + Cfg::STAGES * Cfg::B_STAGE;
+  const uint32_t bar_empty = bar_full + 8 * Cfg::STAGES;
+  const int b = blockIdx.x;
+  int tile = b, i0 = 0;
+  const bool half = b >= p.full_tiles;
+  if (half) {
+    const int r = b - p.full_tiles;
+    tile = p.full_tiles + (r >> 1);
+    i0 = (r & 1) * 4;
+  }
+  const int per_group = p.group_m * p.tiles_n;
+  const int g = tile / per_group;
+  const int first_m = g * p.group_m;
+  const int rows = min(p.group_m, p.tiles_m - first_m);
+  const int rr = tile - g * per_group;
+  const int m0 = (first_m + rr % rows) * Cfg::BM, n0 = (rr / rows) * Cfg::BN;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < Cfg::STAGES; i++) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 8);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (!half) ffma_fat_tile<8>(tmA, tmB, p, m0, n0, 0, sA, sB, bar_full, bar_empty);
+  else       ffma_fat_tile<4>(tmA, tmB, p, m0, n0, i0, sA, sB, bar_full, bar_empty);
+}
+
 }  // namespace b200
