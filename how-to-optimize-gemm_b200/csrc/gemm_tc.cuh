@@ -259,7 +259,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // The whole warp walks the loop (warp-uniform control flow keeps stage/phase/coordinates in uniform
+    // registers, so the UTMALDG operands need no per-lane R2UR waterfall); one elected lane issues.
+    {
       int s = 0;
       uint32_t ph = 0;
       for (int w = unit; w < num_items; w += num_units) {
@@ -275,6 +277,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           // bytes from both CTAs complete on the LEADER's full barrier; only the leader arms it
           const uint32_t full = CG == 2 ? mapa(bar_full + 8 * s, 0) : bar_full + 8 * s;
+          if (elect_one()) {
           if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, tx_bytes);
 #pragma unroll
           for (int pa = 0; pa < Prod::NPA; pa++) {
@@ -293,14 +296,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               else
                 tma_load_2d(dst, &tmB, full, n0 + j * Cfg::B_BOX_COLS, pb * p.b_plane_rows + kb * Cfg::BK);
             }
+          }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && leader) {
-
+    // Same shape as the producer: warp-uniform loop, descriptors live in uniform registers, one elected
+    // lane issues the MMAs and the commits of a k-block.
+    if (leader) {
       const uint32_t b_lbo = p.dbg_b_lbo ? (uint32_t)p.dbg_b_lbo : (uint32_t)Cfg::B_BOX_BYTES;
       const uint32_t b_sbo = p.dbg_b_sbo ? (uint32_t)p.dbg_b_sbo : (uint32_t)T::B_SBO;
       int s = 0;
@@ -320,6 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t a0 = sA + s * Cfg::A_STAGE;
           const uint32_t b0 = sB + s * Cfg::B_STAGE;
+          if (elect_one()) {
 #pragma unroll
           for (int pr = 0; pr < Prod::N; pr++) {
 #pragma unroll
@@ -334,10 +341,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           // frees the smem slot (in both CTAs of a pair) when these MMAs retire
           if constexpr (CG == 2) tc_commit_cg2(bar_empty + 8 * s, 3); else tc_commit(bar_empty + 8 * s);
+          }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         // accumulator complete -> epilogue warps (of both CTAs)
-        if constexpr (CG == 2) tc_commit_cg2(bar_tfull + 8 * as, 3); else tc_commit(bar_tfull + 8 * as);
+        if (elect_one()) {
+          if constexpr (CG == 2) tc_commit_cg2(bar_tfull + 8 * as, 3); else tc_commit(bar_tfull + 8 * as);
+        }
+        __syncwarp();
         if (++as == 2) { as = 0; aph ^= 1; }
        }
       }

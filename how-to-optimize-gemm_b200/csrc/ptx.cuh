@@ -232,6 +232,12 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t c_fmt, uint32_t ab_fm
 //   [0,14) start>>4  [16,30) LBO>>4  [32,46) SBO>>4  [46,48) version=1  [61,64) layout type
 // layout_type: 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms; the only
 // layout the hardware accepts for an MN-major tf32 operand).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_bytes,
                                                uint32_t sbo_bytes, uint32_t layout_type = 2) {
   uint64_t d = 0;
