@@ -272,9 +272,9 @@ int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_tota
 int pick_bn(int m, int n, bool allow256, bool allow192 = true) {
   if (g_force_bn == 128 || (g_force_bn == 192 && allow192) || (g_force_bn == 256 && allow256)) return g_force_bn;
   const int cands[3] = {256, 192, 128};
-  // relative MMA efficiency, measured on B200 at N=4096 (bf16: 1358 / 1230 / 864 TFLOP/s): the
-  // 1-CTA kernel is bound by shared-memory operand reads, which narrower tiles amortise worse
-  const double eff[3] = {1.00, 0.88, 0.62};
+  // relative efficiency of the 1-CTA kernels, measured on B200 at N=4096 (bf16: 1347 / 1317 / 1058
+  // TFLOP/s; the CTA-pair kernel: 1538): narrower tiles amortise shared-memory operand reads worse
+  const double eff[3] = {1.00, 0.97, 0.80};
   int best = 128;
   double best_cost = 1e300;
   const int tm = (m + 127) / 128;
@@ -290,12 +290,15 @@ int pick_bn(int m, int n, bool allow256, bool allow192 = true) {
 }
 
 // CTA pairs (tcgen05 cta_group::2, 256 x BN per pair): each CTA stages only its half of B, halving the
-// shared-memory operand traffic per MMA that bounds the 1-CTA kernel.  Used whenever C has at least
-// two 128-row blocks.
+// shared-memory operand traffic per MMA that bounds the 1-CTA kernel (1538 vs 1347 TFLOP/s, bf16 4096^3).
+// Used once the 256 x 256 pair tiles fill most of the 74 pairs; below that the 1-CTA tiles fill the
+// machine better (N = 1536, BF16X3: 128x128 tiles 143 TFLOP/s, pair tiles 95).
 bool use_pair(int m, int n) {
   if (g_force_cg == 1) return false;
-  if (g_force_cg == 2) return true;
-  return m > 128 && n > 128;
+  if (g_force_cg == 2) return m > 128 && n > 128;
+  if (m <= 128 || n <= 128) return false;
+  const long long tiles = (long long)((m + 255) / 256) * ((n + 255) / 256);
+  return tiles * 5 >= (long long)(g_dev.sms / 2) * 4;
 }
 
 #define TC_PLAIN(KIND, OUT, NAME)                                                                     \
@@ -359,10 +362,17 @@ int gemm_f32_split(int m, int n, int k, const float* A, int lda, const float* B,
   }
   uint16_t* pA = reinterpret_cast<uint16_t*>(g_split_ws.p);
   uint16_t* pB = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(g_split_ws.p) + a_off);
-  const int blocks = g_dev.sms * 8;
-  split_planes_kernel<NP><<<blocks, 256, 0, st>>>(A, lda, m, k, pA, pka, m);
-  split_planes_kernel<NP><<<blocks, 256, 0, st>>>(B, ldb, k, n, pB, pnb, kp);
-  g_launches += 2;
+  {
+    const SplitJob ja{A, lda, m, k, pA, pka, m}, jb{B, ldb, k, n, pB, pnb, kp};
+    const long long wide = pka > pnb ? pka : pnb;
+    const int gx = (int)((wide + 2047) / 2048);
+    int gy = (g_dev.sms * 8 + 2 * gx - 1) / (2 * gx);            // ~8 blocks per SM over both operands
+    const int rows2 = ((m > kp ? m : kp) + 1) / 2;
+    if (gy > rows2) gy = rows2;
+    if (gy < 1) gy = 1;
+    split_planes_kernel<NP><<<dim3(gx, gy, 2), 256, 0, st>>>(ja, jb);
+    g_launches += 1;
+  }
   int rc = last_launch_status();
   if (rc) return rc;
   if (use_pair(m, n)) {

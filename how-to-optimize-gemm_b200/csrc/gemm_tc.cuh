@@ -520,39 +520,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // pitch dld (elements, multiple of 8).  x = p1 + p2 + p3 with p1 = bf16(x), p2 = bf16(x - p1),
 // p3 = bf16(x - p1 - p2); the subtractions are exact in fp32.  Rows [rows, plane_rows) and columns
 // [cols, dld) of every plane are written as zero (K padding of B must contribute nothing).
+struct SplitJob {
+  const float* src; long long ld; int rows, cols;
+  uint16_t* dst; long long dld; int plane_rows;
+};
+
+// One launch splits both operands (blockIdx.z picks A or B).  A thread owns 8 consecutive columns
+// (two 16-byte loads, one 16-byte store per plane) and walks rows blockIdx.y, +gridDim.y, ... two at
+// a time so that 64 B of loads are in flight per thread; HBM-bound: 4 + 2*NP bytes per element.
 template <int NP>
-__global__ void split_planes_kernel(const float* __restrict__ src, long long ld, int rows, int cols,
-                                    uint16_t* __restrict__ dst, long long dld, int plane_rows) {
-  const int cgroups = (int)(dld >> 2);                       // 4 columns per thread
-  const long long total = (long long)plane_rows * cgroups;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(i / cgroups);
-    const int c = (int)(i - (long long)r * cgroups) * 4;
-    float x[4] = {0.f, 0.f, 0.f, 0.f};
-    if (r < rows) {
-      const float* s = src + (long long)r * ld + c;
-      if (c + 4 <= cols && ((reinterpret_cast<uintptr_t>(s) & 15) == 0)) {
-        const float4 v = *reinterpret_cast<const float4*>(s);
-        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-      } else {
+__global__ void __launch_bounds__(256) split_planes_kernel(const SplitJob ja, const SplitJob jb) {
+  const SplitJob& jo = blockIdx.z == 0 ? ja : jb;
+  const float* __restrict__ src = jo.src;
+  uint16_t* __restrict__ dst = jo.dst;
+  const long long ld = jo.ld, dld = jo.dld;
+  const int rows = jo.rows, cols = jo.cols, plane_rows = jo.plane_rows;
+  const int c = (int)(blockIdx.x * 256 + threadIdx.x) * 8;
+  if (c >= dld) return;
+  const bool vec = c + 8 <= cols && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  for (int r0 = blockIdx.y * 2; r0 < plane_rows; r0 += gridDim.y * 2) {
+    float x[2][8];
 #pragma unroll
-        for (int e = 0; e < 4; e++)
-          if (c + e < cols) x[e] = s[e];
+    for (int u = 0; u < 2; u++) {
+      const int r = r0 + u;
+#pragma unroll
+      for (int e = 0; e < 8; e++) x[u][e] = 0.f;
+      if (r < rows) {
+        const float* s = src + (long long)r * ld + c;
+        if (vec) {
+          const float4 v0 = __ldcs(reinterpret_cast<const float4*>(s));
+          const float4 v1 = __ldcs(reinterpret_cast<const float4*>(s) + 1);
+          x[u][0] = v0.x; x[u][1] = v0.y; x[u][2] = v0.z; x[u][3] = v0.w;
+          x[u][4] = v1.x; x[u][5] = v1.y; x[u][6] = v1.z; x[u][7] = v1.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; e++)
+            if (c + e < cols) x[u][e] = s[e];
+        }
       }
     }
 #pragma unroll
-    for (int pl = 0; pl < NP; pl++) {
-      uint16_t h[4];
+    for (int u = 0; u < 2; u++) {
+      const int r = r0 + u;
+      if (r >= plane_rows) break;
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        uint32_t b;
-        asm("{\n\t.reg .b16 t;\n\tcvt.rn.bf16.f32 t, %1;\n\tmov.b32 %0, {t, t};\n\t}" : "=r"(b) : "f"(x[e]));
-        h[e] = (uint16_t)(b & 0xFFFFu);
-        x[e] -= __uint_as_float((uint32_t)h[e] << 16);
+      for (int pl = 0; pl < NP; pl++) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          // packs {hi half <- x[2e+1], lo half <- x[2e]}, round-to-nearest-even
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[e]) : "f"(x[u][2 * e + 1]), "f"(x[u][2 * e]));
+          x[u][2 * e] -= __uint_as_float(w[e] << 16);
+          x[u][2 * e + 1] -= __uint_as_float(w[e] & 0xFFFF0000u);
+        }
+        *reinterpret_cast<uint4*>(dst + ((long long)pl * plane_rows + r) * dld + c) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      uint2 o = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
-      *reinterpret_cast<uint2*>(dst + ((long long)pl * plane_rows + r) * dld + c) = o;
     }
   }
 }
