@@ -23,7 +23,7 @@ EXPORTS = [
     "b200_gemm_version", "b200_gemm_device_ok", "b200_gemm_strerror", "b200_gemm_last_kernel",
     "b200_gemm_launch_count", "b200_gemm_default_f32_mode", "b200_gemm_set_default_f32_mode",
     "b200_gemm_f32", "b200_gemm_f32_acc", "b200_gemm_f32_host", "b200_gemm_bf16", "b200_gemm_s8s32",
-    "b200_gemm_s8s32_host", "b200_convert_f32_to_bf16", "b200_gemm_debug_set_b_desc", "b200_gemm_debug_set_bn",
+    "b200_gemm_s8s32_host", "b200_gemm_s8s8_requant", "b200_convert_f32_to_bf16", "b200_gemm_debug_set_b_desc", "b200_gemm_debug_set_bn",
     "b200_gemm_debug_set_split_chunk", "b200_gemm_debug_kernel_timing", "b200_gemm_debug_kernel_time_ms",
     "b200_gemm_debug_set_cta_group", "b200_gemm_debug_set_split_tail",
 ]
@@ -53,6 +53,7 @@ lib.b200_gemm_f32_host.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i]
 lib.b200_gemm_bf16.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp]
 lib.b200_gemm_s8s32.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]
 lib.b200_gemm_s8s32_host.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i]
+lib.b200_gemm_s8s8_requant.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]
 lib.b200_convert_f32_to_bf16.argtypes = [_vp, _vp, C.c_size_t, _vp]
 lib.b200_gemm_debug_set_b_desc.argtypes = [_i, _i]
 lib.b200_gemm_set_default_f32_mode.argtypes = [_i]
@@ -145,6 +146,25 @@ def gemm_bf16(A, B, out=None, out_dtype=None, stream=None):
     assert out.dtype in (torch.float32, torch.bfloat16)
     _check(lib.b200_gemm_bf16(m, n, k, A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), out.data_ptr(), _ld(out),
                               ot, _stream_ptr(stream)))
+    return out
+
+
+def gemm_s8s8_requant(A, B, scales, bias=None, out=None, stream=None):
+    """int8 x int8 -> int8 with per-row scales / bias (aarch64-int8/int8kernel_m4.S:40,386-426)."""
+    import torch
+    assert A.dtype == torch.int8 and B.dtype == torch.int8 and A.is_cuda and B.is_cuda
+    m, k = A.shape
+    k2, n = B.shape
+    assert k == k2
+    assert scales.dtype == torch.float32 and scales.is_cuda and scales.is_contiguous() and scales.numel() == m
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_cuda and bias.is_contiguous() and bias.numel() == m
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.int8, device=A.device)
+    assert out.dtype == torch.int8
+    _check(lib.b200_gemm_s8s8_requant(m, n, k, A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), out.data_ptr(), _ld(out),
+                                      scales.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                      _stream_ptr(stream)))
     return out
 
 

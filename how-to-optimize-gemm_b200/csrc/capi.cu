@@ -171,6 +171,15 @@ int launch_generic(int m, int n, int k, const InT* A, int lda, const InT* B, int
   return last_launch_status();
 }
 
+int launch_generic_requant(int m, int n, int k, const int8_t* A, int lda, const int8_t* B, int ldb, int8_t* C,
+                           int ldc, const float* scales, const float* bias, cudaStream_t st) {
+  dim3 grid((n + 63) / 64, (m + 63) / 64);
+  gemm_generic_kernel<int8_t, int8_t><<<grid, 256, 0, st>>>(m, n, k, A, lda, B, ldb, C, ldc, 0, scales, bias);
+  g_launches++;
+  t_last_kernel = "generic_s8_requant_64x64";
+  return last_launch_status();
+}
+
 // ---- tensor-core launch -------------------------------------------------------------------
 int g_force_bn = 0;          // test/tuning hook (b200_gemm_debug_set_bn): 0 = heuristic
 int g_group_rows = 0;         // tuning hook: rows per raster group of the tensor-core kernels (0 = 2048)
@@ -332,6 +341,16 @@ int tc_s8(int m, int n, int k, const void* A, int lda, const void* B, int ldb, v
   if (pick_bn(m, n, true, false) == 256)
     return launch_tc<KIND_I8, 256, 4, int32_t>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_s8_128x256");
   return launch_tc<KIND_I8, 128, 6, int32_t>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_s8_128x128");
+}
+
+// int8 in, int8 out through the requantising epilogue (scales / bias ride in the row_max / col_max slots)
+int tc_s8_requant(int m, int n, int k, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
+                  const float* scales, const float* bias, cudaStream_t st) {
+  if (use_pair(m, n))
+    return launch_tc<KIND_I8, 256, 6, s8_out, ProdSingle, 128, 2>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_s8_requant_2cta_256x256", 0, scales, bias);
+  if (pick_bn(m, n, true, false) == 256)
+    return launch_tc<KIND_I8, 256, 4, s8_out>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_s8_requant_128x256", 0, scales, bias);
+  return launch_tc<KIND_I8, 128, 6, s8_out>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_s8_requant_128x128", 0, scales, bias);
 }
 
 // ---- split-precision fp32 on the tensor cores ---------------------------------------------------
@@ -655,6 +674,20 @@ int b200_gemm_s8s32(int m, int n, int k, const int8_t* dA, int lda, const int8_t
   if (!tma_ok(dA, lda, dB, ldb, 1))
     return launch_generic<int8_t, int32_t>(m, n, k, dA, lda, dB, ldb, dC, ldc, 0, st, "generic_s8_64x64");
   return tc_s8(m, n, k, dA, lda, dB, ldb, dC, ldc, st);
+}
+
+int b200_gemm_s8s8_requant(int m, int n, int k, const int8_t* dA, int lda, const int8_t* dB, int ldb,
+                           int8_t* dC, int ldc, const float* dScales, const float* dBias, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = check_args(m, n, k, dA, lda, dB, ldb, dC, ldc);
+  if (rc == 1) return 0;
+  if (rc) return rc;
+  if (!dScales) return B200_ERR_BAD_ARG;
+  rc = ensure_device();
+  if (rc) return rc;
+  if (k == 0 || !tma_ok(dA, lda, dB, ldb, 1))         // K = 0: every element is requant(0) = sat(round(bias))
+    return launch_generic_requant(m, n, k, dA, lda, dB, ldb, dC, ldc, dScales, dBias, st);
+  return tc_s8_requant(m, n, k, dA, lda, dB, ldb, dC, ldc, dScales, dBias, st);
 }
 
 int b200_convert_f32_to_bf16(const float* dSrc, uint16_t* dDst, size_t count, void* stream) {

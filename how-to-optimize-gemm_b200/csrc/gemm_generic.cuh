@@ -10,6 +10,8 @@
 #include <stdint.h>
 #include <type_traits>
 
+#include "ptx.cuh"
+
 namespace b200 {
 
 template <typename T> struct LoadAs;
@@ -29,7 +31,8 @@ template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256)
 gemm_generic_kernel(int M, int N, int K, const InT* __restrict__ A, long long lda,
                     const InT* __restrict__ B, long long ldb, OutT* __restrict__ C, long long ldc,
-                    int accumulate) {
+                    int accumulate, const float* __restrict__ rq_scale = nullptr,
+                    const float* __restrict__ rq_bias = nullptr) {
   using Acc = typename LoadAs<InT>::Acc;
   __shared__ Acc As[16][64 + 4];
   __shared__ Acc Bs[16][64 + 4];
@@ -90,7 +93,15 @@ gemm_generic_kernel(int M, int N, int K, const InT* __restrict__ A, long long ld
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int gn = n0 + tx + 16 * j;
-      if (gn < N) store_out<Acc, OutT>(C + (long long)gm * ldc + gn, acc[i][j]);
+      if (gn < N) {
+        if constexpr (std::is_same<OutT, int8_t>::value && std::is_same<Acc, int32_t>::value) {
+          // requantising store (int8 C): per-row scale and optional per-row bias
+          C[(long long)gm * ldc + gn] = (int8_t)requant_s8(acc[i][j], rq_scale[gm], rq_bias ? rq_bias[gm] : 0.0f,
+                                                            rq_bias != nullptr);
+        } else {
+          store_out<Acc, OutT>(C + (long long)gm * ldc + gn, acc[i][j]);
+        }
+      }
     }
   }
 }

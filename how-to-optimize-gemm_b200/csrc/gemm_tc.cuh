@@ -198,8 +198,15 @@ template <> struct OutPack<bf16_out> {
     for (int i = 0; i < 16; i++) w[16 + i] = cvt2(b[2 * i], b[2 * i + 1]);
   }
 };
+struct s8_out {};     // tag: C stored as int8 through requant_s8 (TcParams::row_max = per-row scale,
+                      // TcParams::col_max = per-row bias or null); int8 kernels only
+template <> struct OutPack<s8_out> {
+  static constexpr int COLS = 32;
+  __device__ static void pack(const uint32_t (&)[32], const uint32_t (&)[32], uint32_t (&)[32]) {}
+};
 template <typename OutT> struct OutBytes { static constexpr int V = 4; };
 template <> struct OutBytes<bf16_out> { static constexpr int V = 2; };
+template <> struct OutBytes<s8_out> { static constexpr int V = 1; };
 
 template <int KIND, int BN, int STAGES, typename OutT, class Prod, int A_ROW_BYTES, int CG>
 __global__ void __launch_bounds__(192, 1)
@@ -369,6 +376,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tile_coords(it.tile, p.tiles_m, p.tiles_n, p.group_m, mb, nb);
       const int m0 = mb * Cfg::TILE_M + (int)cta_rank * Cfg::BM + q * 32, n0 = nb * BN + it.nsub * it.bn;
       const int passes = it.bn / COLS;
+      // requant: this lane's row keeps one scale / bias for the whole tile (fetched before the wait on the accumulator)
+      float sc = 0.0f, bi = 0.0f;
+      bool hb = false;
+      if constexpr (std::is_same<OutT, s8_out>::value) {
+        hb = p.col_max != nullptr;
+        if (m0 + lane < p.M) {
+          sc = __ldg(p.row_max + m0 + lane);
+          if (hb) bi = __ldg(p.col_max + m0 + lane);
+        }
+      }
       int* flag = p.flags + ((it.tile - p.full_tiles) * CG + (int)cta_rank) * 4 + q;
       if (it.part > 0) {                               // wait until parts < it.part are in C
         if (lane == 0) {
@@ -392,6 +409,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::ACC_STRIDE;
 #pragma unroll 1
       for (int ps = 0; ps < passes; ps++) {
+       if constexpr (std::is_same<OutT, s8_out>::value) {
+        // Requantising epilogue: lane = row, 32 accumulator columns -> 32 bytes, stored straight from
+        // registers as two 16-byte vectors (whole 32-byte sectors; no staging transpose needed).
+        uint32_t ra[32];
+        tmem_ld_32x32b_x32(t_addr + ps * 32, ra);
+        tmem_ld_wait();
+        if (ps == passes - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_cluster(tempty_base + 8 * as);
+            else mbar_arrive(bar_tempty + 8 * as);
+          }
+        }
+        const int gm = m0 + lane, col0 = n0 + ps * 32;
+        if (gm < p.M && col0 < p.N) {
+          uint32_t w8[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+              v |= ((uint32_t)requant_s8((int32_t)ra[4 * j + e], sc, bi, hb) & 0xFFu) << (8 * e);
+            w8[j] = v;
+          }
+          uint8_t* dst = reinterpret_cast<uint8_t*>(p.C) + (long long)gm * p.ldc + col0;
+          if (p.vec_ok && col0 + 32 <= p.N) {
+            reinterpret_cast<uint4*>(dst)[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+            reinterpret_cast<uint4*>(dst)[1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; e++)
+              if (col0 + e < p.N) dst[e] = (uint8_t)(w8[e >> 2] >> (8 * (e & 3)));
+          }
+        }
+       } else {
         const int chunk = lane & 7;
         const int col = n0 + ps * COLS + chunk * VEC_ELEMS;
         const bool vec = p.vec_ok && col + VEC_ELEMS <= p.N;
@@ -492,6 +545,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         __syncwarp();
+       }
       }
       if (++as == 2) { as = 0; aph ^= 1; }
      }

@@ -232,6 +232,24 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t c_fmt, uint32_t ab_fm
 //   [0,14) start>>4  [16,30) LBO>>4  [32,46) SBO>>4  [46,48) version=1  [61,64) layout type
 // layout_type: 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms; the only
 // layout the hardware accepts for an MN-major tf32 operand).
+// int32 accumulator -> int8, the arithmetic of chgemm's requant tail (aarch64-int8/int8kernel_m4.S:386-426):
+// scvtf (int32 -> fp32, RNE), fmul by the row's scale, optional fadd of the row's bias (two roundings, not
+// fused), fcvtas (to nearest, ties AWAY from zero, saturating, NaN -> 0), sqxtn x2 (saturate to int8).
+__device__ __forceinline__ int32_t requant_s8(int32_t acc, float scale, float bias, bool has_bias) {
+  float f = __fmul_rn(__int2float_rn(acc), scale);
+  if (has_bias) f = __fadd_rn(f, bias);
+  // Everything below is exact fp32 arithmetic on the FMA pipe (no F2I / FRND conversions, which run at a
+  // quarter of the rate): clamp (results beyond +-200 saturate anyway), round to nearest-even with the
+  // 1.5 * 2^23 constant, then move exact ties that went towards zero one step away from it.
+  const float g = fminf(fmaxf(f, -200.0f), 200.0f);
+  const float magic = 12582912.0f;
+  float r = __fadd_rn(__fadd_rn(g, magic), -magic);
+  if (fabsf(__fadd_rn(g, -r)) == 0.5f && fabsf(r) < fabsf(g)) r = __fadd_rn(r, copysignf(1.0f, g));
+  r = fminf(fmaxf(r, -128.0f), 127.0f);
+  const int32_t q = __float_as_int(__fadd_rn(r, magic)) - 0x4B400000;
+  return f != f ? 0 : q;
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));

@@ -15,6 +15,8 @@
  *   b200_gemm_s8s32   <- aarch64-int8/MMult_4x8_21.c:81-86 (12-arg MY_MMult,
  *                        int8 x int8 -> int32, C = A*B, any m,n,k)
  *   b200_gemm_s8s32_host <- aarch64-int8/test_MMult.c:9,98 (host pointers)
+ *   b200_gemm_s8s8_requant <- aarch64-int8/int8kernel_m4.S:40 (int8kernel_m4_requant:
+ *                        int8 x int8 -> int8 through per-row scales / bias, :386-426)
  *
  * All matrices are ROW-MAJOR: A is m x k (leading dimension lda >= k),
  * B is k x n (ldb >= n), C is m x n (ldc >= n); leading dimensions are in
@@ -128,6 +130,18 @@ int b200_gemm_s8s32(int m, int n, int k,
 int b200_gemm_s8s32_host(int m, int n, int k,
                          const int8_t* A, int lda, const int8_t* B, int ldb,
                          int32_t* C, int ldc);
+
+/* int8 x int8 -> int8 with the requantising tail of chgemm's kernels fused into the
+ * GEMM epilogue (aarch64-int8/int8kernel_m4.S:386-426; signature :40):
+ *   C(i,j) = sat_int8( round_ties_away( float(sum_p A(i,p)*B(p,j)) * dScales[i] (+ dBias[i]) ) )
+ * int32 -> fp32 conversion rounds to nearest even, the multiply and the add round
+ * separately (fmul, fadd), NaN converts to 0.  dScales has m entries, dBias has m
+ * entries or is NULL (the kernel's `cmp bias, #0`).  C is written once as int8
+ * (1 byte per element instead of 4).  DEVICE pointers; ldc in elements (bytes). */
+int b200_gemm_s8s8_requant(int m, int n, int k,
+                           const int8_t* dA, int lda, const int8_t* dB, int ldb,
+                           int8_t* dC, int ldc, const float* dScales,
+                           const float* dBias, void* stream);
 
 /* Element-wise helper the bf16 config needs on the device: round-to-nearest-
  * even fp32 -> bf16 (the rounding SURVEY §8d prescribes for config 3 inputs). */

@@ -188,6 +188,26 @@ void oracle_ref_mmult_s8s32_fast(int m, int n, int k, const int8_t* a, int lda,
   par_rows(m, rows_s8, &x);
 }
 
+/* aarch64-int8/int8kernel_m4.S:386-426.  One C statement per instruction; built with -ffp-contract=off so
+ * the fmul / fadd pair stays two roundings as in the assembly. */
+void oracle_requant_s32_to_s8(int m, int n, const int32_t* c, int ldc, const float* scales,
+                              const float* bias, int8_t* out, int ldo) {
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < n; j++) {
+      float f = (float)c[(size_t)i * ldc + j];          /* scvtf  :389 (round to nearest even) */
+      f = f * scales[i];                                /* fmul   :394, scale of the ROW (v12.s[i]) */
+      if (bias) f = f + bias[i];                        /* fadd   :405, skipped when bias == NULL :399-400 */
+      int32_t r;                                        /* fcvtas :415 nearest, ties away, saturating, NaN -> 0 */
+      if (f != f) r = 0;
+      else {
+        float t = roundf(f);
+        r = t >= 2147483648.0f ? INT32_MAX : t <= -2147483648.0f ? INT32_MIN : (int32_t)t;
+      }
+      int16_t h = r > 32767 ? 32767 : r < -32768 ? -32768 : (int16_t)r;   /* sqxtn .4h :420 */
+      out[(size_t)i * ldo + j] = h > 127 ? 127 : h < -128 ? -128 : (int8_t)h;   /* sqxtn .8b :425 */
+    }
+}
+
 /* cuda/compare_matrices.cpp:17-29, NaN-aware. */
 float oracle_compare_matrices_f32(int m, int n, const float* a, int lda,
                                   const float* b, int ldb) {

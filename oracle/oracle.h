@@ -69,6 +69,14 @@ void oracle_ref_mmult_s8s32(int m, int n, int k, const int8_t* a, int lda,
 void oracle_ref_mmult_s8s32_fast(int m, int n, int k, const int8_t* a, int lda,
                                  const int8_t* b, int ldb, int32_t* c, int ldc);
 
+/* Requant tail of chgemm's kernels, aarch64-int8/int8kernel_m4.S:386-426 (same in _m2 :647-684, _m1 :851-):
+ * out(i,j) = sqxtn(sqxtn(fcvtas(fadd(fmul(scvtf(c(i,j)), scales[i]), bias[i])))) ; bias may be NULL (:399-400).
+ * PARITY UNPINNED for this function: the reference ships no C caller, test or vector for the requant
+ * kernels and the .S files are AArch64-only, so this restates the instruction sequence and nothing here
+ * can be checked against the reference running. */
+void oracle_requant_s32_to_s8(int m, int n, const int32_t* c, int ldc, const float* scales,
+                              const float* bias, int8_t* out, int ldo);
+
 /* ---- checkers --------------------------------------------------------------- */
 /* cuda/compare_matrices.cpp:7-30: max_ij |A(i,j)-B(i,j)| (row-major).  Unlike
  * the reference's macro abs (Appendix B-7) a NaN anywhere returns NaN. */

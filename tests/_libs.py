@@ -100,6 +100,20 @@ def ref_s8(o, a, b):
     return c
 
 
+def requant_s8(o, c32, scales, bias=None):
+    """oracle_requant_s32_to_s8 over an int32 matrix (aarch64-int8/int8kernel_m4.S:386-426)."""
+    c32 = np.ascontiguousarray(c32, np.int32)
+    m, n = c32.shape
+    scales = np.ascontiguousarray(scales, np.float32)
+    out = np.zeros((m, n), np.int8)
+    bp = None
+    if bias is not None:
+        bias = np.ascontiguousarray(bias, np.float32)
+        bp = P(bias)
+    o.oracle_requant_s32_to_s8(m, n, P(c32), n, P(scales), bp, P(out), n)
+    return out
+
+
 def gen_s8(o, m, n, seed):
     a = np.zeros((m, n), np.int8)
     o.oracle_random_int8_uniform(m, n, P(a), n, seed)

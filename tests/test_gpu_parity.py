@@ -174,6 +174,81 @@ def test_s8_extremes_and_alignment(gemm, oracle):
     assert np.array_equal(c_cc, _libs.ref_s8(oracle, a[:, 1:k + 1], b[1:k + 1, 1:n + 1]))
 
 
+def _rq_case(oracle, m, n, k, seed, kind):
+    a, b = _libs.gen_s8(oracle, m, k, seed), _libs.gen_s8(oracle, k, n, seed + 1)
+    rng = np.random.default_rng(seed)
+    if kind == "ties":          # power-of-two scales: every odd accumulator lands exactly on a .5 tie
+        scales = np.float32(2.0) ** -rng.integers(1, 9, m).astype(np.float32)
+        bias = (rng.integers(-8, 9, m) * 0.5).astype(np.float32)
+    elif kind == "saturate":    # most products leave [-128, 127]
+        scales = rng.uniform(0.01, 0.5, m).astype(np.float32)
+        bias = rng.uniform(-300, 300, m).astype(np.float32)
+    else:                       # what a quantised layer passes: |acc| ~ 127^2 sqrt(k) / 3 mapped to ~[-100, 100]
+        scales = (rng.uniform(0.5, 2.0, m) * 300.0 / (127.0 ** 2 * max(k, 1) ** 0.5)).astype(np.float32)
+        bias = rng.uniform(-20, 20, m).astype(np.float32)
+    return a, b, scales, bias
+
+
+@pytest.mark.parametrize("kind", ["ties", "saturate", "layer"])
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (300, 528, 208), (77, 96, 80), (512, 1024, 1024),
+                                   (1000, 1104, 2048), (2304, 2304, 512)])
+def test_s8_requant_bit_exact(gemm, oracle, m, n, k, kind):
+    """int8 out through the fused requant epilogue == oracle_requant(REF_MMult int32) bit for bit
+    (aarch64-int8/int8kernel_m4.S:386-426), with and without bias, tensor-core and generic paths."""
+    a, b, scales, bias = _rq_case(oracle, m, n, k, 61, kind)
+    c32 = _libs.ref_s8(oracle, a, b)
+    A, B, S, Bi = cuda(a), cuda(b), cuda(scales), cuda(bias)
+    out = gemm.gemm_s8s8_requant(A, B, S, Bi).cpu().numpy()
+    assert gemm.last_kernel().startswith("tc_s8_requant"), gemm.last_kernel()
+    assert np.array_equal(out, _libs.requant_s8(oracle, c32, scales, bias))
+    out = gemm.gemm_s8s8_requant(A, B, S, None).cpu().numpy()            # bias == NULL (cmp bias, #0)
+    assert np.array_equal(out, _libs.requant_s8(oracle, c32, scales, None))
+    if kind == "ties":
+        assert (out != np.clip(np.rint(c32 * scales[:, None]), -128, 127)).any()   # ties-to-even would differ
+
+
+def test_s8_requant_generic_path_and_edges(gemm, oracle):
+    m, n, k = 130, 208, 112            # + 16: pitches 224 and 128 bytes, TMA-able when the base is aligned
+    a, b, scales, bias = _rq_case(oracle, m, n + 16, k + 16, 71, "ties")
+    A, B, S, Bi = cuda(a), cuda(b), cuda(scales), cuda(bias)
+    out = gemm.gemm_s8s8_requant(A[:, 1:k + 1], B[1:k + 1, 1:n + 1], S, Bi).cpu().numpy()   # misaligned bases
+    assert gemm.last_kernel().startswith("generic_s8_requant")
+    ref = _libs.requant_s8(oracle, _libs.ref_s8(oracle, a[:, 1:k + 1], b[1:k + 1, 1:n + 1]), scales, bias)
+    assert np.array_equal(out, ref)
+    # output pitch that is not a multiple of 16 bytes: byte stores on the tensor-core path
+    Cbig = torch.zeros((m, n + 3), dtype=torch.int8, device="cuda")
+    gemm.gemm_s8s8_requant(A[:, :96], B[:96, :n], S, Bi, out=Cbig[:, :n])
+    assert gemm.last_kernel().startswith("tc_s8_requant")
+    ref = _libs.requant_s8(oracle, _libs.ref_s8(oracle, a[:, :96], b[:96, :n]), scales, bias)
+    assert np.array_equal(Cbig[:, :n].cpu().numpy(), ref) and (Cbig[:, n:] == 0).all()
+    # K = 0: every element is requant(0) = sat(round_away(bias)); NaN / inf scales
+    out = gemm.gemm_s8s8_requant(A[:, :0], B[:0, :n], S, Bi).cpu().numpy()
+    assert np.array_equal(out, _libs.requant_s8(oracle, np.zeros((m, n), np.int32), scales, bias))
+    weird = scales.copy()
+    weird[0], weird[1], weird[2] = np.nan, np.inf, -np.inf
+    out = gemm.gemm_s8s8_requant(A[:, :96], B[:96, :n], cuda(weird), None).cpu().numpy()
+    assert np.array_equal(out, _libs.requant_s8(oracle, _libs.ref_s8(oracle, a[:, :96], b[:96, :n]), weird, None))
+    assert (out[0] == 0).all()
+
+
+def test_full_size_s8_requant_4096(gemm, oracle):
+    N = 4096
+    a, b, scales, bias = _rq_case(oracle, N, N, N, 81, "layer")
+    A, B, S, Bi = cuda(a), cuda(b), cuda(scales), cuda(bias)
+    out = gemm.gemm_s8s8_requant(A, B, S, Bi)
+    assert gemm.last_kernel() == "tc_s8_requant_2cta_256x256"
+    rows = np.arange(0, N, 31)[:128]
+    ref = _libs.requant_s8(oracle, _libs.ref_s8(oracle, a[rows], b), scales[rows], bias[rows])
+    assert np.array_equal(out[torch.from_numpy(rows).cuda()].cpu().numpy(), ref)
+    # whole matrix against the library's own int32 product requantised on the device with torch (fp32 ops,
+    # round-half-away written out): the fused epilogue and the two-pass route agree everywhere
+    c32 = gemm.gemm_s8s32(A, B)
+    f = c32.float() * S[:, None] + Bi[:, None]
+    t = torch.trunc(f)
+    t = torch.where((f - t).abs() >= 0.5, t + torch.sign(f), t).clamp(-128, 127).to(torch.int8)
+    assert torch.equal(out, t)
+
+
 def test_empty_and_k_zero(gemm):
     A = torch.zeros((0, 8), device="cuda")
     B = torch.zeros((8, 5), device="cuda")

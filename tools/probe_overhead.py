@@ -28,8 +28,23 @@ def t_us(fn, reps=20, warm=5):
     return best
 
 
-for n in [int(x) for x in sys.argv[1:]] or [4096]:
+S8 = "--s8" in sys.argv
+for n in [int(x) for x in sys.argv[1:] if x.isdigit()] or [4096]:
     rows = []
+    if S8:
+        for k in (512, 1024, 2048, 4096, 8192, 16384):
+            A = torch.randint(-127, 128, (n, k), device=dev, dtype=torch.int8)
+            B = torch.randint(-127, 128, (k, n), device=dev, dtype=torch.int8)
+            C = torch.empty(n, n, device=dev, dtype=torch.int32)
+            us = t_us(lambda: g.gemm_s8s32(A, B, out=C))
+            cub = t_us(lambda: torch._int_mm(A, B, out=C))
+            rows.append((k, us, cub))
+            print(f"N={n} K={k:6d}  ours s8 {us:8.1f} us {2.0*n*n*k/us/1e6:7.0f} TOPS | torch._int_mm {cub:8.1f} us {2.0*n*n*k/cub/1e6:7.0f} TOPS  {g.last_kernel()}", flush=True)
+        (k0, a0, c0), (k1, a1, c1) = rows[1], rows[-1]
+        for name, x0, x1 in (("ours s8", a0, a1), ("int_mm", c0, c1)):
+            slope = (x1 - x0) / (k1 - k0)
+            print(f"  {name}: per-1024-K {slope*1024:.2f} us, fixed {x0 - slope*k0:.2f} us, asymptotic {2.0*n*n/slope/1e6:.0f} TOPS")
+        continue
     for k in (256, 512, 1024, 2048, 4096, 8192, 16384):
         A = (torch.rand(n, k, device=dev) - 0.5).bfloat16()
         B = (torch.rand(k, n, device=dev) - 0.5).bfloat16()
