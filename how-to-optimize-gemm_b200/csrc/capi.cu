@@ -184,6 +184,7 @@ int launch_generic_requant(int m, int n, int k, const int8_t* A, int lda, const 
 int g_force_bn = 0;          // test/tuning hook (b200_gemm_debug_set_bn): 0 = heuristic
 int g_group_rows = 0;         // tuning hook: rows per raster group of the tensor-core kernels (0 = 2048)
 int g_force_cg = 0;
+int g_epi_direct = 0;       // tuning hook (b200_gemm_debug_set_epilogue): 1 = direct register stores for non-folding passes
 int g_ffma_fat = -1;        // strict kernel: 1 = 128x256 fat-thread variant, 0 = 128x128, -1 = by size
 int g_ffma_halves = 1;      // strict kernel: split the tail round into half tiles (tuning hook)          // test/tuning hook (b200_gemm_debug_set_cta_group): 0 = auto, 1, 2
 
@@ -219,6 +220,7 @@ int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_tota
   p.dbg_b_lbo = g_dbg_b_lbo; p.dbg_b_sbo = g_dbg_b_sbo;
   p.row_max = row_max; p.col_max = col_max;
   p.accumulate = accumulate;
+  p.epi_direct = g_epi_direct;
   auto kern = gemm_tc_kernel<KIND, BN, STAGES, OutT, Prod, A_ROW_BYTES, CG>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -613,6 +615,7 @@ void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes) { g_dbg_b_lbo = lb
 void b200_gemm_debug_set_bn(int bn) { g_force_bn = bn; }
 void b200_gemm_debug_set_cta_group(int cg) { g_force_cg = cg; }
 void b200_gemm_debug_set_split_tail(int on) { g_split_tail = on; }
+void b200_gemm_debug_set_epilogue(int direct) { g_epi_direct = direct; }
 void b200_gemm_debug_set_group_rows(int rows) { g_group_rows = rows; }
 void b200_gemm_debug_set_ffma_variant(int v) { g_ffma_halves = v & 1; g_ffma_fat = v < 0 ? -1 : (v >> 1) & 1; }
 void b200_gemm_debug_set_split_chunk(int x3_k, int x2_k) { g_split_chunk_k[0] = x3_k; g_split_chunk_k[1] = x2_k; }
