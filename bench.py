@@ -231,8 +231,12 @@ def main():
     rp = None
     if world > 1:
         rowpanel = __import__("importlib").import_module(_libs.PKG + ".rowpanel")
+        slices = BCAST_CHUNKS if args.workload == "headline" else 4
+        if os.environ.get("B200_BCAST_SLICES"):        # tuning: "3" = three balanced slices, "1,3,4" = weighted
+            v = [int(x) for x in os.environ["B200_BCAST_SLICES"].split(",")]
+            slices = v[0] if len(v) == 1 else tuple(v)
         rp = rowpanel.RowPanelGemm(lambda a, b, out, acc: g.gemm_f32(a, b, out=out, mode=mode, accumulate=acc), dist, rank, world,
-                                   K, N, BCAST_CHUNKS if args.workload == "headline" else 4, dev, torch.float32)
+                                   K, N, slices, dev, torch.float32)
 
     def step(i):
         A, B, Cm, _ = sets[i % R]
@@ -313,7 +317,7 @@ def main():
         "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": MODE_DTYPE.get(mode, str(mode)), "data": "synthetic",
         "config": {"workload": f"fp32 SGEMM row-major M={Mloc * world} N=K={N} (BASELINE configs[{1 if args.workload == 'headline' else 4}]); "
-                               f"C row-panel sharded, B broadcast from rank 0 inside every step as {BCAST_CHUNKS} K-slices (NCCL, in place) pipelined with the K-sliced GEMM" if world > 1 else
+                               f"C row-panel sharded, B broadcast from rank 0 inside every step as {len(rp.chunks) if rp else 0} K-slices {[k1 - k0 for k0, k1 in rp.chunks] if rp else ""} (NCCL, in place) pipelined with the K-sliced GEMM" if world > 1 else
                                f"fp32 SGEMM row-major M=N=K={N0} (BASELINE configs[1], N=4096 point)",
                    "precision_mode": MODE_NAMES.get(mode, str(mode)), "kernel": kernel_name,
                    "l2": f"{R} rotating input/output sets of {3 * N0 * N0 * 4 / 1e6:.0f} MB each (> 126 MB L2 between reuses)",

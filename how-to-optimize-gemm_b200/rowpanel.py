@@ -27,10 +27,25 @@ def row_panel(rank, world, M):
     return r0, r0 + base + (1 if rank < extra else 0)
 
 
-def row_chunks(K, chunks):
-    """Balanced split of the K rows of B into `chunks` contiguous blocks."""
-    chunks = max(1, min(chunks, K))
-    return [row_panel(i, chunks, K) for i in range(chunks)]
+def row_chunks(K, chunks, align=64):
+    """Split of the K rows of B into contiguous blocks: an int gives that many balanced blocks, a sequence
+    gives blocks proportional to its weights with boundaries rounded to `align` rows (whole k-blocks).  A small
+    first block shortens the only part of the broadcast the math cannot hide behind: (1, 3, 4) on K = 4096
+    is 512 / 1536 / 2048 rows."""
+    if isinstance(chunks, int):
+        chunks = max(1, min(chunks, K))
+        return [row_panel(i, chunks, K) for i in range(chunks)]
+    w = [float(x) for x in chunks if x > 0]
+    tot, acc, edges = sum(w), 0.0, [0]
+    for x in w[:-1]:
+        acc += x
+        e = int(round(K * acc / tot / align)) * align
+        e = min(max(e, edges[-1]), K)
+        if e > edges[-1]:
+            edges.append(e)
+    if edges[-1] < K:
+        edges.append(K)
+    return list(zip(edges[:-1], edges[1:]))
 
 
 class RowPanelGemm:

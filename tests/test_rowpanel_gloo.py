@@ -59,6 +59,15 @@ def test_rowpanel_world2(tmp_path, oracle, M, N, K, panel):
     assert np.array_equal(C, _libs.ref_f32_fma(oracle, a, b))
 
 
+@pytest.mark.parametrize("world,M,N,K,panel", [(4, 41, 24, 200, (1, 3, 4)), (3, 10, 16, 130, 2)])
+def test_rowpanel_world_gt2(tmp_path, oracle, world, M, N, K, panel):
+    """More ranks than the GPU validation had (the driver's scaling run goes to 8), weighted K-slices."""
+    mp.spawn(_worker, args=(world, _free_port(), M, N, K, panel, str(tmp_path)), nprocs=world, join=True)
+    C = np.concatenate([np.load(tmp_path / f"c_{r}.npy") for r in range(world)], axis=0)
+    a, b = _libs.gen_f32(oracle, M, K, 100), _libs.gen_f32(oracle, K, N, 200)
+    assert np.array_equal(C, _libs.ref_f32_fma(oracle, a, b))
+
+
 def test_partition_helpers():
     import importlib
     sys.path.insert(0, _libs.ROOT)
@@ -73,3 +82,10 @@ def test_partition_helpers():
     assert rowpanel.row_chunks(4096, 4) == [(0, 1024), (1024, 2048), (2048, 3072), (3072, 4096)]
     assert rowpanel.row_chunks(10, 3) == [(0, 4), (4, 7), (7, 10)]
     assert rowpanel.row_chunks(2, 8) == [(0, 1), (1, 2)]
+    assert rowpanel.row_chunks(4096, (1, 3, 4)) == [(0, 512), (512, 2048), (2048, 4096)]
+    assert rowpanel.row_chunks(200, (1, 3, 4)) == [(0, 128), (128, 200)]        # 25 rows round to no block
+    for K in (1, 63, 64, 200, 4096, 16384):
+        for w in ((1, 3, 4), (1, 1), (5,), (1, 2, 2, 3)):
+            ch = rowpanel.row_chunks(K, w)
+            assert ch[0][0] == 0 and ch[-1][1] == K and all(a < b for a, b in ch)
+            assert all(ch[i][1] == ch[i + 1][0] for i in range(len(ch) - 1))
