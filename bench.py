@@ -406,7 +406,7 @@ def main():
             sweep.append([n, round(2.0 * n ** 3 / (s.elapsed_time(e) / 20) / 1e6, 2)])
             sweep_kernels.append(g.last_kernel())
         out["sweep"] = sweep
-        out["sweep_kernels"] = sweep_kernels       # AUTO takes the single-launch strict kernel below ~1024^3
+        out["sweep_kernels"] = sweep_kernels       # AUTO takes the single-launch strict kernel up to ~512^3
         out["cpu_baseline"] = cpu_baseline(o)
     _phase("extras done")
     print(json.dumps(out))

@@ -560,10 +560,11 @@ int gemm_f32_impl(int m, int n, int k, const float* dA, int lda, const float* dB
   const bool was_auto = mode == B200_F32_AUTO;
   mode = resolve_f32_mode(mode);
   const bool tma = tma_ok(dA, lda, dB, ldb, 4);
-  // AUTO on a small problem: the split path costs three launches (two pre-pass + GEMM) and cannot
-  // fill 74 CTA pairs; below ~1024^3 the single-launch strict FFMA2 kernel is both faster (measured:
-  // 40 vs 33.5 TFLOP/s at 1024^3, 9.2 vs 6.9 at 512^3) and bit-exact against the reference oracle.
-  if (was_auto && mode == B200_F32_BF16X3 && tma && (double)m * n * k <= 1.1e9) mode = B200_F32_STRICT;
+  // AUTO on a small problem: the split path costs two launches (pre-pass + GEMM); up to 512^3 the
+  // single-launch strict FFMA2 kernel is within 15 % of it (measured, tools/probe_small.py: 9.3 vs 10.6
+  // TFLOP/s at 512^3, 2.0 vs 2.0 at 256^3) and bit-exact against the reference oracle.  From 640^3 the
+  // tensor-core path pulls away (19.2 vs 15.0; 63.0 vs 41.0 at 1024^3).
+  if (was_auto && mode == B200_F32_BF16X3 && tma && (double)m * n * k <= 2.0e8) mode = B200_F32_STRICT;
   switch (mode) {
     case B200_F32_STRICT:
       // 128x256 fat-thread tiles once they fill most of the machine (measured at N = 4096 / 3072 / 2048:

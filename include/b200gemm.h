@@ -62,7 +62,7 @@ enum b200_f32_mode {
   B200_F32_BF16X2 = 3,   /* split-bf16: a=a1+a2, 3 products, ~2^-17 relative       */
   B200_F32_AUTO   = 4,   /* library default: BF16X3 unless the environment variable
                             B200GEMM_F32_MODE or b200_gemm_set_default_f32_mode
-                            says otherwise; problems below ~1024^3 with TMA-able
+                            says otherwise; problems up to ~512^3 with TMA-able
                             operands take the single-launch STRICT kernel          */
   B200_F32_F16X2  = 5    /* scaled split-fp16: rows of A / columns of B are scaled by
                             exact powers of two into [-1,1], a'=h1+h2 in fp16 (22
