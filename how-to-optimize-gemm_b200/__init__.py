@@ -25,7 +25,8 @@ EXPORTS = [
     "b200_gemm_f32", "b200_gemm_f32_acc", "b200_gemm_f32_host", "b200_gemm_bf16", "b200_gemm_s8s32",
     "b200_gemm_s8s32_host", "b200_gemm_s8s8_requant", "b200_convert_f32_to_bf16", "b200_gemm_debug_set_b_desc", "b200_gemm_debug_set_bn",
     "b200_gemm_debug_set_split_chunk", "b200_gemm_debug_kernel_timing", "b200_gemm_debug_kernel_time_ms",
-    "b200_gemm_debug_set_cta_group", "b200_gemm_debug_set_split_tail",
+    "b200_gemm_debug_set_cta_group", "b200_gemm_debug_set_split_tail", "b200_gemm_debug_set_group_rows",
+    "b200_gemm_debug_set_ffma_variant", "b200_gemm_debug_set_epilogue",
 ]
 
 

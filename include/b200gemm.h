@@ -162,6 +162,14 @@ void b200_gemm_debug_set_split_tail(int on);
 /* Tuning hook: K extent the tensor core accumulates before the epilogue folds the partial sum
  * into C with a rounded fp32 add (two-level accumulation of the split modes); 0 = whole K. */
 void b200_gemm_debug_set_split_chunk(int bf16x3_k, int bf16x2_k);
+/* Tuning hook: rows of A per raster group of the persistent tile schedule (0 = 2048). */
+void b200_gemm_debug_set_group_rows(int rows);
+/* Tuning hook for the strict fp32 kernels: bit 0 = half tiles in the last partial round (default on),
+ * bit 1 = force the 128x256 fat-thread kernel; a negative value restores selection by size. */
+void b200_gemm_debug_set_ffma_variant(int v);
+/* Tuning hook: 1 = non-folding epilogue passes store straight from registers instead of through the
+ * shared-memory transpose (measured no faster on B200; default 0). */
+void b200_gemm_debug_set_epilogue(int direct);
 /* Measurement hook: while enabled, a CUDA-event pair is recorded on the launching stream around
  * every dominant GEMM kernel launch (not the split pre-pass).  b200_gemm_debug_kernel_time_ms
  * synchronises those events, stores the summed kernel time and returns the number of launches

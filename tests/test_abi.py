@@ -32,6 +32,13 @@ def test_library_exports_every_declared_symbol(gemm):
     assert sorted(gemm.EXPORTS) == declared_functions()
 
 
+def test_library_exports_nothing_undeclared(gemm):
+    """Every b200_* symbol the shared object exports is declared (and documented) in the header."""
+    out = subprocess.check_output(["nm", "-D", "--defined-only", gemm.LIB_PATH], text=True)
+    exported = sorted({ln.split()[-1] for ln in out.splitlines() if " T b200_" in ln})
+    assert exported == declared_functions()
+
+
 def test_no_undefined_oracle_or_blas_dependencies(gemm):
     """The product must not link the oracle, the reference, cuBLAS or any BLAS."""
     out = subprocess.check_output(["ldd", gemm.LIB_PATH], text=True)
@@ -71,6 +78,9 @@ def test_argument_validation(gemm):
     assert lib.b200_gemm_f32(0, 4, 4, None, 4, None, 4, None, 4, 0, None) == 0        # empty: no-op
     assert lib.b200_gemm_s8s32(4, 0, 4, None, 4, None, 4, None, 4, None) == 0
     assert lib.b200_gemm_bf16(4, 4, 4, buf, 4, buf, 4, buf, 4, 7, None) == -1         # bad out_type
+    assert lib.b200_gemm_s8s8_requant(4, 4, 4, buf, 4, buf, 4, buf, 4, None, None, None) == -1   # scales are required
+    assert lib.b200_gemm_s8s8_requant(4, 4, 4, buf, 4, buf, 4, buf, 3, buf, None, None) == -1    # ldc < n
+    assert lib.b200_gemm_s8s8_requant(0, 4, 4, None, 4, None, 4, None, 4, None, None, None) == 0  # empty: no-op
     assert b"bad argument" in lib.b200_gemm_strerror(-1)
 
 
