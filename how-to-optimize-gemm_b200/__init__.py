@@ -23,7 +23,8 @@ EXPORTS = [
     "b200_gemm_version", "b200_gemm_device_ok", "b200_gemm_strerror", "b200_gemm_last_kernel",
     "b200_gemm_launch_count", "b200_gemm_default_f32_mode", "b200_gemm_set_default_f32_mode",
     "b200_gemm_f32", "b200_gemm_f32_acc", "b200_gemm_f32_host", "b200_gemm_bf16", "b200_gemm_s8s32",
-    "b200_gemm_s8s32_host", "b200_gemm_s8s8_requant", "b200_convert_f32_to_bf16", "b200_gemm_debug_set_b_desc", "b200_gemm_debug_set_bn",
+    "b200_gemm_s8s32_host", "b200_gemm_s8s8_requant", "b200_gemm_f32_pack_b", "b200_gemm_f32_packed",
+    "b200_gemm_f32_pack_free", "b200_convert_f32_to_bf16", "b200_gemm_debug_set_b_desc", "b200_gemm_debug_set_bn",
     "b200_gemm_debug_set_split_chunk", "b200_gemm_debug_kernel_timing", "b200_gemm_debug_kernel_time_ms",
     "b200_gemm_debug_set_cta_group", "b200_gemm_debug_set_split_tail", "b200_gemm_debug_set_group_rows",
     "b200_gemm_debug_set_ffma_variant", "b200_gemm_debug_set_epilogue",
@@ -54,6 +55,10 @@ lib.b200_gemm_f32_host.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i]
 lib.b200_gemm_bf16.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp]
 lib.b200_gemm_s8s32.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]
 lib.b200_gemm_s8s32_host.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i]
+lib.b200_gemm_f32_pack_b.argtypes = [_i, _i, _vp, _i, _i, C.POINTER(_vp), _vp]
+lib.b200_gemm_f32_packed.argtypes = [_i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp]
+lib.b200_gemm_f32_pack_free.argtypes = [_vp]
+lib.b200_gemm_f32_pack_free.restype = None
 lib.b200_gemm_s8s8_requant.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]
 lib.b200_convert_f32_to_bf16.argtypes = [_vp, _vp, C.c_size_t, _vp]
 lib.b200_gemm_debug_set_b_desc.argtypes = [_i, _i]
@@ -147,6 +152,41 @@ def gemm_bf16(A, B, out=None, out_dtype=None, stream=None):
     assert out.dtype in (torch.float32, torch.bfloat16)
     _check(lib.b200_gemm_bf16(m, n, k, A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), out.data_ptr(), _ld(out),
                               ot, _stream_ptr(stream)))
+    return out
+
+
+class PackedB:
+    """Pre-split B (b200_gemm_f32_pack_b): holds the handle, frees it with the object."""
+
+    def __init__(self, B, mode=F32_AUTO, stream=None):
+        import torch
+        assert B.dtype == torch.float32 and B.is_cuda and B.dim() == 2
+        self.k, self.n = B.shape
+        self.handle = _vp()
+        _check(lib.b200_gemm_f32_pack_b(self.k, self.n, B.data_ptr(), _ld(B), mode, C.byref(self.handle),
+                                        _stream_ptr(stream)))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib.b200_gemm_f32_pack_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown: module globals may already be gone
+            pass
+
+
+def gemm_f32_packed(A, packedB, out=None, stream=None, accumulate=False):
+    import torch
+    assert A.dtype == torch.float32 and A.is_cuda
+    m, k = A.shape
+    if out is None:
+        assert not accumulate
+        out = torch.empty((m, packedB.n), dtype=torch.float32, device=A.device)
+    _check(lib.b200_gemm_f32_packed(m, packedB.n, k, A.data_ptr(), _ld(A), packedB.handle, out.data_ptr(), _ld(out),
+                                    1 if accumulate else 0, _stream_ptr(stream)))
     return out
 
 

@@ -378,29 +378,38 @@ int split_ws_reserve(size_t need, cudaStream_t st) {
   return B200_OK;
 }
 
+// Plane geometry shared by the per-call pre-pass and the pre-split B handle (b200_gemm_f32_pack_b).
+inline long long plane_pitch(int cols) { return ((long long)cols + 7) & ~7LL; }   // elements, 16-byte multiple
+inline int b_plane_rows(int k) { return (k + 31) & ~31; }                           // zero rows pad K to the k-block
+
+// Splits one operand (jobs == 1) or both (jobs == 2) in a single launch.
+template <int NP>
+int launch_split(const SplitJob& ja, const SplitJob& jb, int jobs, cudaStream_t st) {
+  const long long wide = jobs == 2 && jb.dld > ja.dld ? jb.dld : ja.dld;
+  const int tall = jobs == 2 && jb.plane_rows > ja.plane_rows ? jb.plane_rows : ja.plane_rows;
+  const int gx = (int)((wide + 2047) / 2048);
+  int gy = (g_dev.sms * 8 + jobs * gx - 1) / (jobs * gx);        // ~8 blocks per SM over the launch
+  if (gy > (tall + 1) / 2) gy = (tall + 1) / 2;
+  if (gy < 1) gy = 1;
+  split_planes_kernel<NP><<<dim3(gx, gy, jobs), 256, 0, st>>>(ja, jb);
+  g_launches += 1;
+  return last_launch_status();
+}
+
+// prepB: bf16 planes of B split earlier by b200_gemm_f32_pack_b (then only A is split here), or null.
 template <int NP>
 int gemm_f32_split(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                   cudaStream_t st, int acc = 0) {
-  const long long pka = ((long long)k + 7) & ~7LL;          // A plane pitch (elements), 16-byte multiple
-  const long long pnb = ((long long)n + 7) & ~7LL;          // B plane pitch
-  const int kp = (k + 31) & ~31;                            // B plane height: zero rows pad K to the k-block
+                   cudaStream_t st, int acc = 0, const uint16_t* prepB = nullptr) {
+  const long long pka = plane_pitch(k), pnb = plane_pitch(n);
+  const int kp = b_plane_rows(k);
   const size_t a_bytes = (size_t)NP * m * pka * 2, b_bytes = (size_t)NP * kp * pnb * 2;
   const size_t a_off = (a_bytes + 1023) & ~(size_t)1023;
-  if (int rc = split_ws_reserve(a_off + b_bytes, st)) return rc;
+  if (int rc = split_ws_reserve(prepB ? a_off : a_off + b_bytes, st)) return rc;
   uint16_t* pA = reinterpret_cast<uint16_t*>(g_split_ws.p);
-  uint16_t* pB = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(g_split_ws.p) + a_off);
-  {
-    const SplitJob ja{A, lda, m, k, pA, pka, m}, jb{B, ldb, k, n, pB, pnb, kp};
-    const long long wide = pka > pnb ? pka : pnb;
-    const int gx = (int)((wide + 2047) / 2048);
-    int gy = (g_dev.sms * 8 + 2 * gx - 1) / (2 * gx);            // ~8 blocks per SM over both operands
-    const int rows2 = ((m > kp ? m : kp) + 1) / 2;
-    if (gy > rows2) gy = rows2;
-    if (gy < 1) gy = 1;
-    split_planes_kernel<NP><<<dim3(gx, gy, 2), 256, 0, st>>>(ja, jb);
-    g_launches += 1;
-  }
-  int rc = last_launch_status();
+  const uint16_t* pB = prepB ? prepB
+                             : reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(g_split_ws.p) + a_off);
+  const SplitJob ja{A, lda, m, k, pA, pka, m}, jb{B, ldb, k, n, const_cast<uint16_t*>(pB), pnb, kp};
+  int rc = launch_split<NP>(ja, jb, prepB ? 1 : 2, st);
   if (rc) return rc;
   if (use_pair(m, n)) {
     if constexpr (NP == 3)
@@ -678,6 +687,52 @@ int b200_gemm_s8s32(int m, int n, int k, const int8_t* dA, int lda, const int8_t
   if (!tma_ok(dA, lda, dB, ldb, 1))
     return launch_generic<int8_t, int32_t>(m, n, k, dA, lda, dB, ldb, dC, ldc, 0, st, "generic_s8_64x64");
   return tc_s8(m, n, k, dA, lda, dB, ldb, dC, ldc, st);
+}
+
+// ---- pre-split B (the reference's "packAB interface is open" idea, README.md:85, for the split modes) ----
+struct b200_packed_b {
+  int k, n, np, kp;
+  long long pnb;
+  uint16_t* planes;
+};
+
+int b200_gemm_f32_pack_b(int k, int n, const float* dB, int ldb, int precision_mode, b200_packed_b** out,
+                         void* stream) {
+  if (!out) return B200_ERR_BAD_ARG;
+  *out = nullptr;
+  if (k <= 0 || n <= 0 || !dB || ldb < n) return B200_ERR_BAD_ARG;
+  const int mode = resolve_f32_mode(precision_mode);
+  if (mode != B200_F32_BF16X3 && mode != B200_F32_BF16X2) return B200_ERR_UNSUPPORTED;
+  int rc = ensure_device();
+  if (rc) return rc;
+  b200_packed_b* h = new b200_packed_b{k, n, mode == B200_F32_BF16X3 ? 3 : 2, b_plane_rows(k), plane_pitch(n), nullptr};
+  cudaError_t e = cudaMalloc(&h->planes, (size_t)h->np * h->kp * h->pnb * 2);
+  if (e != cudaSuccess) { cudaGetLastError(); delete h; return (int)e; }
+  const SplitJob jb{dB, ldb, k, n, h->planes, h->pnb, h->kp};
+  rc = h->np == 3 ? launch_split<3>(jb, jb, 1, (cudaStream_t)stream) : launch_split<2>(jb, jb, 1, (cudaStream_t)stream);
+  t_last_kernel = "split_planes";
+  if (rc) { cudaFree(h->planes); delete h; return rc; }
+  *out = h;
+  return B200_OK;
+}
+
+int b200_gemm_f32_packed(int m, int n, int k, const float* dA, int lda, const b200_packed_b* pb, float* dC,
+                         int ldc, int accumulate, void* stream) {
+  if (!pb || pb->k != k || pb->n != n) return B200_ERR_BAD_ARG;
+  int rc = check_args(m, n, k, dA, lda, pb->planes, n, dC, ldc);
+  if (rc == 1) return 0;
+  if (rc) return rc;
+  rc = ensure_device();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  return pb->np == 3 ? gemm_f32_split<3>(m, n, k, dA, lda, nullptr, 0, dC, ldc, st, accumulate ? 1 : 0, pb->planes)
+                     : gemm_f32_split<2>(m, n, k, dA, lda, nullptr, 0, dC, ldc, st, accumulate ? 1 : 0, pb->planes);
+}
+
+void b200_gemm_f32_pack_free(b200_packed_b* pb) {
+  if (!pb) return;
+  if (pb->planes) cudaFree(pb->planes);
+  delete pb;
 }
 
 int b200_gemm_s8s8_requant(int m, int n, int k, const int8_t* dA, int lda, const int8_t* dB, int ldb,

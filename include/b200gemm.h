@@ -131,6 +131,23 @@ int b200_gemm_s8s32_host(int m, int n, int k,
                          const int8_t* A, int lda, const int8_t* B, int ldb,
                          int32_t* C, int ldc);
 
+/* Pre-split B for the split-precision modes (BF16X3 / BF16X2; AUTO = the library default): the
+ * reference leaves its "packAB interface open" for callers that reuse one operand (README.md:85;
+ * PackMatrixB, aarch64/MMult_4x4_13.cpp:361).  TMA needs no repacking of row-major B, but the fp32 ->
+ * bf16-plane split of B is per-call work (half of the pre-pass) that a constant B can pay once.
+ * b200_gemm_f32_pack_b splits the k x n matrix into a handle that owns its device memory;
+ * b200_gemm_f32_packed computes C = A*B (accumulate = 0) or C += A*B (1) with it and is bit-identical
+ * to b200_gemm_f32 / b200_gemm_f32_acc in the handle's mode.  DEVICE pointers; the handle may be used
+ * by any number of later calls (stream-ordered after the pack call) and is released with
+ * b200_gemm_f32_pack_free.  Modes without a split (STRICT, TF32, F16X2) return B200_ERR_UNSUPPORTED. */
+typedef struct b200_packed_b b200_packed_b;
+int b200_gemm_f32_pack_b(int k, int n, const float* dB, int ldb, int precision_mode,
+                         b200_packed_b** out, void* stream);
+int b200_gemm_f32_packed(int m, int n, int k, const float* dA, int lda,
+                         const b200_packed_b* packedB, float* dC, int ldc,
+                         int accumulate, void* stream);
+void b200_gemm_f32_pack_free(b200_packed_b* packedB);
+
 /* int8 x int8 -> int8 with the requantising tail of chgemm's kernels fused into the
  * GEMM epilogue (aarch64-int8/int8kernel_m4.S:386-426; signature :40):
  *   C(i,j) = sat_int8( round_ties_away( float(sum_p A(i,p)*B(p,j)) * dScales[i] (+ dBias[i]) ) )

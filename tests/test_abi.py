@@ -81,6 +81,11 @@ def test_argument_validation(gemm):
     assert lib.b200_gemm_s8s8_requant(4, 4, 4, buf, 4, buf, 4, buf, 4, None, None, None) == -1   # scales are required
     assert lib.b200_gemm_s8s8_requant(4, 4, 4, buf, 4, buf, 4, buf, 3, buf, None, None) == -1    # ldc < n
     assert lib.b200_gemm_s8s8_requant(0, 4, 4, None, 4, None, 4, None, 4, None, None, None) == 0  # empty: no-op
+    h = C.c_void_p()
+    assert lib.b200_gemm_f32_pack_b(4, 4, None, 4, 2, C.byref(h), None) == -1 and not h.value   # null B
+    assert lib.b200_gemm_f32_pack_b(4, 4, buf, 4, 0, C.byref(h), None) == -3                     # STRICT has no split
+    assert lib.b200_gemm_f32_packed(4, 4, 4, buf, 4, None, buf, 4, 0, None) == -1                # null handle
+    lib.b200_gemm_f32_pack_free(None)                                                            # no-op
     assert b"bad argument" in lib.b200_gemm_strerror(-1)
 
 

@@ -249,6 +249,47 @@ def test_full_size_s8_requant_4096(gemm, oracle):
     assert torch.equal(out, t)
 
 
+@pytest.mark.parametrize("mode", ["x3", "x2"])
+@pytest.mark.parametrize("m,n,k", [(300, 520, 200), (77, 96, 80), (1000, 1104, 2048), (2304, 2304, 1024)])
+def test_f32_packed_b_bit_identical(gemm, oracle, m, n, k, mode):
+    """b200_gemm_f32_pack_b + b200_gemm_f32_packed == b200_gemm_f32 / _acc in the same mode, bit for bit
+    (same planes, same kernel), for several A against one handle (the reuse the packing interface is for)."""
+    md = {"x3": gemm.F32_BF16X3, "x2": gemm.F32_BF16X2}[mode]
+    b = _libs.gen_f32(oracle, k, n, 52)
+    B = cuda(b)
+    pk = gemm.PackedB(B, md)
+    for seed in (51, 53):
+        A = cuda(_libs.gen_f32(oracle, m, k, seed))
+        ref = gemm.gemm_f32(A, B, mode=md)
+        k_ref = gemm.last_kernel()
+        out = gemm.gemm_f32_packed(A, pk)
+        assert gemm.last_kernel() == k_ref
+        assert torch.equal(out, ref)
+    C0 = cuda(_libs.gen_f32(oracle, m, n, 54))
+    C1, C2 = C0.clone(), C0.clone()
+    gemm.gemm_f32(A, B, out=C1, mode=md, accumulate=True)
+    gemm.gemm_f32_packed(A, pk, out=C2, accumulate=True)
+    assert torch.equal(C1, C2)
+    t = _libs.ref_f64(oracle, A.cpu().numpy(), b)
+    assert rel(out.cpu().numpy(), t) <= (TOL_X3 if mode == "x3" else TOL_X2)
+    pk.close()
+
+
+def test_f32_packed_b_errors(gemm):
+    B = torch.rand(64, 48, device="cuda")
+    A = torch.rand(32, 64, device="cuda")
+    for md in (gemm.F32_STRICT, gemm.F32_TF32, gemm.F32_F16X2):
+        with pytest.raises(gemm.B200GemmError) as e:
+            gemm.PackedB(B, md)
+        assert e.value.code == -3                                   # no split in these modes
+    pk = gemm.PackedB(B)                                            # AUTO = library default (BF16X3)
+    assert torch.equal(gemm.gemm_f32_packed(A, pk), gemm.gemm_f32(A, B, mode=gemm.F32_BF16X3))
+    with pytest.raises(gemm.B200GemmError) as e:
+        gemm.gemm_f32_packed(torch.rand(32, 80, device="cuda"), pk)  # k does not match the handle
+    assert e.value.code == -1
+    assert gemm.gemm_f32_packed(torch.rand(0, 64, device="cuda"), pk).shape == (0, 48)
+
+
 def test_empty_and_k_zero(gemm):
     A = torch.zeros((0, 8), device="cuda")
     B = torch.zeros((8, 5), device="cuda")
