@@ -183,10 +183,10 @@ int launch_generic_requant(int m, int n, int k, const int8_t* A, int lda, const 
 // ---- tensor-core launch -------------------------------------------------------------------
 int g_force_bn = 0;          // test/tuning hook (b200_gemm_debug_set_bn): 0 = heuristic
 int g_group_rows = 0;         // tuning hook: rows per raster group of the tensor-core kernels (0 = 2048)
-int g_force_cg = 0;
-int g_epi_direct = 0;       // tuning hook (b200_gemm_debug_set_epilogue): 1 = direct register stores for non-folding passes
-int g_ffma_fat = -1;        // strict kernel: 1 = 128x256 fat-thread variant, 0 = 128x128, -1 = by size
-int g_ffma_halves = 1;      // strict kernel: split the tail round into half tiles (tuning hook)          // test/tuning hook (b200_gemm_debug_set_cta_group): 0 = auto, 1, 2
+int g_force_cg = 0;           // test/tuning hook (b200_gemm_debug_set_cta_group): 0 = auto, 1, 2
+int g_epi_direct = 0;         // tuning hook (b200_gemm_debug_set_epilogue): 1 = direct register stores for non-folding passes
+int g_ffma_fat = -1;          // strict kernel: 1 = 128x256 fat-thread variant, 0 = 128x128, -1 = by size
+int g_ffma_halves = 1;        // strict kernel: split the tail round into half tiles (tuning hook)
 
 template <int KIND, int BN, int STAGES, typename OutT, class Prod = ProdSingle, int A_ROW_BYTES = 128, int CG = 1>
 int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_total, int a_plane_rows,
