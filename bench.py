@@ -23,9 +23,29 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-# stdout must carry exactly one JSON line: whatever NCCL_DEBUG level the box sets (its version
-# banner included) goes to stderr
+# stdout must carry exactly one JSON line.  NCCL prints its version banner with a C-level printf to
+# fd 1 on the first communicator (seen on the 2-GPU box even with NCCL_DEBUG_FILE set), so the real
+# stdout is set aside at start-up, fd 1 is pointed at stderr for everything else this process or its
+# libraries print, and the JSON line alone is written to the saved descriptor.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_JSON_FD = None
+
+
+def _claim_stdout():
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    sys.stdout.flush()
+    data = (json.dumps(obj) + "\n").encode()
+    fd = _JSON_FD if _JSON_FD is not None else 1
+    while data:
+        data = data[os.write(fd, data):]
+
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 N0 = 4096                     # headline size
@@ -125,14 +145,14 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     gf = 2.0 * M * N0 * N0 / dt / 1e9
     sample = f"{args.steps} full SGEMMs M={M} N=K={N0} ({what}), {threads} threads"
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": "SGEMM GFLOP/s (square N=4096 point of the 256..4096 sweep)", "value": gf,
         "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"fp32 SGEMM row-major M={M} N=K={N0} (BASELINE configs[1], N=4096 point)"},
         "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------
@@ -192,6 +212,7 @@ def main():
                     help="headline: M=4096*gpus, N=K=4096 (weak).  c5: BASELINE configs[4], M=N=K=16384 "
                          "row-panel sharded over the ranks (strong); not the driver's default")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -304,9 +325,9 @@ def main():
            "h2d_bytes_per_step": (Mloc * K + K * N + Mloc * N) * 4, "d2h_bytes_per_step": Mloc * N * 4,
            "ms_per_step": e2e_ms, "api": "b200_gemm_f32_host (9-arg MY_MMult contract, pinned host buffers, per rank)"}
 
+    if world > 1:
+        dist.destroy_process_group()        # every rank, right after the last collective
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
     _phase("e2e done")
@@ -409,7 +430,7 @@ def main():
         out["sweep_kernels"] = sweep_kernels       # AUTO takes the single-launch strict kernel up to ~512^3
         out["cpu_baseline"] = cpu_baseline(o)
     _phase("extras done")
-    print(json.dumps(out))
+    _emit(out)
 
 
 if __name__ == "__main__":
