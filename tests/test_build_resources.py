@@ -1,0 +1,52 @@
+"""Resource budget of the compiled kernels, from the `-Xptxas -v` log the in-tree build writes
+(how-to-optimize-gemm_b200/build_ptxas.log): the occupancy each kernel is designed for only holds
+while these stay true.  CPU only (ptxas cross-compiles sm_100a without a GPU)."""
+import os
+import re
+
+import _libs
+
+LOG = os.path.join(_libs.ROOT, _libs.PKG, "build_ptxas.log")
+
+
+def kernels():
+    out, name = {}, None
+    for line in open(LOG):
+        m = re.search(r"Compiling entry function '(\w+)' for 'sm_100a'", line)
+        if m:
+            name = m.group(1)
+            out[name] = {"regs": None, "spill": None}
+        elif name and "spill stores" in line:
+            out[name]["spill"] = int(re.search(r"(\d+) bytes spill stores", line).group(1))
+        elif name and "Used" in line and "registers" in line:
+            out[name]["regs"] = int(re.search(r"Used (\d+) registers", line).group(1))
+    return out
+
+
+def test_log_covers_every_kernel_family():
+    k = kernels()
+    for frag in ["gemm_tc_kernel", "gemm_ffma_kernel", "gemm_ffma_fat_kernel", "gemm_generic_kernel", "split_planes_kernel"]:
+        assert any(frag in n for n in k), frag
+    assert all(v["regs"] is not None and v["spill"] is not None for v in k.values())
+
+
+def test_tensor_core_kernels_do_not_spill():
+    # 192 threads, one CTA per SM: up to 255 registers are free, a spill would sit in the epilogue's inner loop
+    for n, v in kernels().items():
+        if "gemm_tc_kernel" in n:
+            assert v["spill"] == 0 and v["regs"] <= 255, (n, v)
+
+
+def test_strict_kernels_keep_their_occupancy():
+    k = kernels()
+    thin = next(v for n, v in k.items() if "gemm_ffma_kernel" in n)
+    fat = next(v for n, v in k.items() if "gemm_ffma_fat_kernel" in n)
+    assert thin["regs"] <= 128           # 256 threads x 2 CTAs/SM x 128 = the whole register file
+    assert thin["spill"] <= 64           # the C += entry's prologue only; the k loop must stay in registers
+    assert fat["regs"] <= 255 and fat["spill"] == 0
+
+
+def test_prepass_kernels_allow_full_occupancy():
+    for n, v in kernels().items():
+        if "split_planes_kernel" in n:
+            assert v["regs"] <= 64 and v["spill"] == 0, (n, v)      # 8 blocks of 256 threads per SM
