@@ -24,7 +24,10 @@ EXPORTS = [
     "b200_gemm_launch_count", "b200_gemm_default_f32_mode", "b200_gemm_set_default_f32_mode",
     "b200_gemm_f32", "b200_gemm_f32_acc", "b200_gemm_f32_host", "b200_gemm_bf16", "b200_gemm_s8s32",
     "b200_gemm_s8s32_host", "b200_gemm_s8s8_requant", "b200_gemm_f32_pack_b", "b200_gemm_f32_packed",
-    "b200_gemm_f32_pack_free", "b200_convert_f32_to_bf16", "b200_gemm_debug_set_b_desc", "b200_gemm_debug_set_bn",
+    "b200_gemm_f32_pack_free", "b200_nccl_load", "b200_nccl_last_error", "b200_comm_unique_id", "b200_comm_init_rank",
+    "b200_comm_destroy", "b200_rowpanel_create", "b200_rowpanel_destroy", "b200_rowpanel_slices", "b200_gemm_f32_rowpanel",
+    "b200_gemm_f32_rowpanel_host", "b200_gemm_f32_pack_a", "b200_gemm_f32_packed_ab", "b200_gemm_f32_pack_free_a",
+    "b200_convert_f32_to_bf16", "b200_gemm_debug_set_b_desc", "b200_gemm_debug_set_bn",
     "b200_gemm_debug_set_split_chunk", "b200_gemm_debug_kernel_timing", "b200_gemm_debug_kernel_time_ms",
     "b200_gemm_debug_set_cta_group", "b200_gemm_debug_set_split_tail", "b200_gemm_debug_set_group_rows",
     "b200_gemm_debug_set_ffma_variant", "b200_gemm_debug_set_epilogue",
@@ -59,6 +62,21 @@ lib.b200_gemm_f32_pack_b.argtypes = [_i, _i, _vp, _i, _i, C.POINTER(_vp), _vp]
 lib.b200_gemm_f32_packed.argtypes = [_i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp]
 lib.b200_gemm_f32_pack_free.argtypes = [_vp]
 lib.b200_gemm_f32_pack_free.restype = None
+lib.b200_gemm_f32_pack_a.argtypes = [_i, _i, _vp, _i, _i, C.POINTER(_vp), _vp]
+lib.b200_gemm_f32_packed_ab.argtypes = [_i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp]
+lib.b200_gemm_f32_pack_free_a.argtypes = [_vp]
+lib.b200_gemm_f32_pack_free_a.restype = None
+lib.b200_nccl_load.argtypes = [C.c_char_p]
+lib.b200_nccl_last_error.restype = C.c_char_p
+lib.b200_comm_unique_id.argtypes = [_vp]
+lib.b200_comm_init_rank.argtypes = [C.POINTER(_vp), _vp, _i, _i]
+lib.b200_comm_destroy.argtypes = [_vp]
+lib.b200_rowpanel_create.argtypes = [C.POINTER(_vp), _vp, _i, _i, _i, _i, C.POINTER(_i), _i]
+lib.b200_rowpanel_destroy.argtypes = [_vp]
+lib.b200_rowpanel_destroy.restype = None
+lib.b200_rowpanel_slices.argtypes = [_vp, C.POINTER(_i), _i]
+lib.b200_gemm_f32_rowpanel.argtypes = [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp]
+lib.b200_gemm_f32_rowpanel_host.argtypes = [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i]
 lib.b200_gemm_s8s8_requant.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]
 lib.b200_convert_f32_to_bf16.argtypes = [_vp, _vp, C.c_size_t, _vp]
 lib.b200_gemm_debug_set_b_desc.argtypes = [_i, _i]
@@ -80,7 +98,10 @@ def kernel_time_ms():
 
 def _check(rc):
     if rc != 0:
-        raise B200GemmError(rc, lib.b200_gemm_strerror(rc).decode())
+        what = lib.b200_gemm_strerror(rc).decode()
+        if rc == -5:
+            what += ": " + lib.b200_nccl_last_error().decode()
+        raise B200GemmError(rc, what)
 
 
 def version():
@@ -176,6 +197,36 @@ class PackedB:
             self.close()
         except Exception:      # interpreter shutdown: module globals may already be gone
             pass
+
+
+class PackedA:
+    """Pre-split A (b200_gemm_f32_pack_a, F16X2): holds the handle, frees it with the object."""
+
+    def __init__(self, A, mode=F32_AUTO, stream=None):
+        import torch
+        assert A.dtype == torch.float32 and A.is_cuda and A.dim() == 2
+        self.m, self.k = A.shape
+        self.handle = _vp()
+        _check(lib.b200_gemm_f32_pack_a(self.m, self.k, A.data_ptr(), _ld(A), mode, C.byref(self.handle),
+                                        _stream_ptr(stream)))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib.b200_gemm_f32_pack_free_a(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def gemm_f32_packed_ab(packedA, packedB, out, a_k0=0, stream=None, accumulate=False):
+    """C (+)= A[:, a_k0:a_k0+k] * B from two pre-split operands (b200_gemm_f32_packed_ab)."""
+    _check(lib.b200_gemm_f32_packed_ab(packedA.m, packedB.n, packedB.k, packedA.handle, a_k0, packedB.handle,
+                                       out.data_ptr(), _ld(out), 1 if accumulate else 0, _stream_ptr(stream)))
+    return out
 
 
 def gemm_f32_packed(A, packedB, out=None, stream=None, accumulate=False):

@@ -26,8 +26,6 @@ namespace {
 
 std::atomic<unsigned long long> g_launches{0};
 int g_split_tail = 1;        // test/tuning hook (b200_gemm_debug_set_split_tail): 0 = whole tiles only
-int* g_flags = nullptr;      // tail-split ordering flags (zero between launches), 16 rotating slots of 1024 ints
-unsigned g_flag_slot = 0;
 
 // Optional per-launch timing of the dominant GEMM kernel (bench.py's roofline.achieved): a pair of
 // CUDA events is recorded on the launching stream around the kernel.  Off by default.
@@ -51,13 +49,56 @@ std::atomic<int> g_default_f32_mode{-1};
 thread_local const char* t_last_kernel = "none";
 int g_dbg_b_lbo = 0, g_dbg_b_sbo = 0;
 
-struct DeviceInfo {
+// ---- per-device state ------------------------------------------------------------------------------
+// Everything the library caches on a GPU lives in the context of THAT device (flags, split workspace,
+// host-path staging buffers and streams, which kernels already had their dynamic shared memory limit
+// raised), so one process may drive several GPUs (one host thread or one stream per GPU).  The split
+// workspace is shared by all streams of a device: users are serialised by ws_mu on the host and by an
+// event recorded after the consuming GEMM on the device (a call on another stream waits for it).
+struct Scratch { void* p = nullptr; size_t bytes = 0; };
+struct HostPipe {
+  bool ready = false;
+  cudaStream_t h2d = nullptr, comp = nullptr, d2h = nullptr;
+  cudaEvent_t in[8] = {}, done[8] = {};
+  cudaError_t init() {
+    if (ready) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    for (int i = 0; i < 8; i++) {
+      if ((e = cudaEventCreateWithFlags(&in[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+      if ((e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    ready = true;
+    return cudaSuccess;
+  }
+};
+struct DevCtx {
   int ok = 0;          // 1 usable, -1 not usable, 0 unknown
   int sms = 0;
   int dev = -1;
+  int* flags = nullptr;      // tail-split ordering flags (zero between launches), 16 rotating slots of 1024 ints
+  unsigned flag_slot = 0;
+  // split-precision workspace (planes of A and B, row / column maxima): cached, grow-only
+  std::mutex ws_mu;
+  Scratch ws;
+  cudaEvent_t ws_event = nullptr;    // recorded after the last GEMM that read the workspace
+  cudaStream_t ws_stream = nullptr;  // stream of that GEMM
+  bool ws_busy = false;
+  unsigned cmax_slot = 0;            // F16X2: double-buffered column maxima (the idle one is re-zeroed by the pre-pass)
+  float* cmax_buf = nullptr;
+  size_t cmax_cap = 0;
+  int cmax_dirty[2] = {0, 0};       // entries of each half that may be non-zero
+  // host-pointer entry points
+  std::mutex host_mu;
+  Scratch scr[4];
+  HostPipe pipe;
+  std::vector<const void*> attr_done;   // kernels whose MaxDynamicSharedMemorySize was raised on this device
 };
+constexpr int kMaxDevices = 64;
+DevCtx g_ctx[kMaxDevices];
 std::mutex g_mu;
-DeviceInfo g_dev;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -65,33 +106,57 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 
+thread_local DevCtx* t_ctx = nullptr;   // context of the device current on this thread (set by ensure_device)
+
+// Binds t_ctx to the CUDA device current on the calling thread, initialising its context on first use.
 int ensure_device() {
-  std::lock_guard<std::mutex> lk(g_mu);
   int dev = -1;
-  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); g_dev.ok = -1; return B200_ERR_NO_DEVICE; }
-  if (g_dev.ok == 1 && g_dev.dev == dev) return 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { cudaGetLastError(); t_ctx = nullptr; return B200_ERR_NO_DEVICE; }
+  DevCtx* c = &g_ctx[dev];
+  t_ctx = c;
+  if (c->ok == 1) return 0;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (c->ok == 1) return 0;
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { cudaGetLastError(); g_dev.ok = -1; return B200_ERR_NO_DEVICE; }
-  if (prop.major != 10) { g_dev.ok = -1; return B200_ERR_NO_DEVICE; }
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { cudaGetLastError(); c->ok = -1; return B200_ERR_NO_DEVICE; }
+  if (prop.major != 10) { c->ok = -1; return B200_ERR_NO_DEVICE; }
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
         qres != cudaDriverEntryPointSuccess || !fn) {
       cudaGetLastError();
-      g_dev.ok = -1;
+      c->ok = -1;
       return B200_ERR_NO_DEVICE;
     }
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  if (!g_flags) {
-    if (cudaMalloc(&g_flags, 16 * 1024 * sizeof(int)) != cudaSuccess || cudaMemset(g_flags, 0, 16 * 1024 * sizeof(int)) != cudaSuccess) {
-      cudaGetLastError(); g_flags = nullptr; g_dev.ok = -1; return B200_ERR_NO_DEVICE;
+  if (!c->flags) {
+    if (cudaMalloc(&c->flags, 16 * 1024 * sizeof(int)) != cudaSuccess || cudaMemset(c->flags, 0, 16 * 1024 * sizeof(int)) != cudaSuccess) {
+      cudaGetLastError(); c->flags = nullptr; c->ok = -1; return B200_ERR_NO_DEVICE;
     }
   }
-  g_dev.ok = 1;
-  g_dev.dev = dev;
-  g_dev.sms = prop.multiProcessorCount;
+  if (!c->ws_event && cudaEventCreateWithFlags(&c->ws_event, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError(); c->ok = -1; return B200_ERR_NO_DEVICE;
+  }
+  c->dev = dev;
+  c->sms = prop.multiProcessorCount;
+  c->ok = 1;
+  return 0;
+}
+
+// Raises a kernel's dynamic shared memory limit once per (kernel, device).
+template <typename Kern>
+int ensure_smem_attr(Kern kern, int bytes) {
+  const void* key = reinterpret_cast<const void*>(kern);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (const void* k : t_ctx->attr_done) if (k == key) return 0;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+  std::lock_guard<std::mutex> lk(g_mu);
+  t_ctx->attr_done.push_back(key);
   return 0;
 }
 
@@ -113,7 +178,7 @@ constexpr size_t kMapCache = 64;
 int get_map(CUtensorMap* out, const void* ptr, CUtensorMapDataType dt, int elem_bytes,
             unsigned long long inner, unsigned long long rows, unsigned long long ld_bytes,
             unsigned box_inner, unsigned box_rows, int swizzle /*0 none, 1 = 128B, 2 = 128B atom 32B, 3 = 64B*/) {
-  MapKey key{ptr, (int)dt, inner, rows, ld_bytes, box_inner, box_rows, swizzle, g_dev.dev};
+  MapKey key{ptr, (int)dt, inner, rows, ld_bytes, box_inner, box_rows, swizzle, t_ctx->dev};
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto& e : g_maps)
     if (e.key == key) { *out = e.map; return 0; }
@@ -222,14 +287,9 @@ int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_tota
   p.accumulate = accumulate;
   p.epi_direct = g_epi_direct;
   auto kern = gemm_tc_kernel<KIND, BN, STAGES, OutT, Prod, A_ROW_BYTES, CG>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
-    attr_set = true;
-  }
+  if (int arc = ensure_smem_attr(kern, Cfg::SMEM_BYTES)) return arc;
   int tiles = p.tiles_m * p.tiles_n;
-  const int units_max = g_dev.sms / CG;                 // CTAs, or CTA pairs (one per TPC)
+  const int units_max = t_ctx->sms / CG;                 // CTAs, or CTA pairs (one per TPC)
   // Wave quantisation: the last, partial round of tiles (or the only round of a small problem) is
   // cut along K so that every CTA/pair has work: rem tiles x split parts <= units.
   const int num_kb = (k + Cfg::BK - 1) / Cfg::BK;
@@ -253,7 +313,7 @@ int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_tota
   }
   p.split = split;
   p.full_tiles = (split > 1 || p.halfn) ? tiles - rem : tiles;
-  p.flags = g_flags + (g_flag_slot++ % 16) * 1024;
+  p.flags = t_ctx->flags + (t_ctx->flag_slot++ % 16) * 1024;
   const int items = p.full_tiles + (tiles - p.full_tiles) * (p.halfn ? 2 : split);
   const int units = items < units_max ? items : units_max;
   g_ktimer.begin(st);
@@ -293,7 +353,7 @@ int pick_bn(int m, int n, bool allow256, bool allow192 = true) {
     if (cands[i] == 256 && !allow256) continue;
     if (cands[i] == 192 && !allow192) continue;
     const long long tiles = (long long)tm * ((n + cands[i] - 1) / cands[i]);
-    const long long waves = (tiles + g_dev.sms - 1) / g_dev.sms;
+    const long long waves = (tiles + t_ctx->sms - 1) / t_ctx->sms;
     const double cost = (double)waves * (cands[i] / eff[i] + 8.0);
     if (cost < best_cost) { best_cost = cost; best = cands[i]; }
   }
@@ -309,7 +369,7 @@ bool use_pair(int m, int n) {
   if (g_force_cg == 2) return m > 128 && n > 128;
   if (m <= 128 || n <= 128) return false;
   const long long tiles = (long long)((m + 255) / 256) * ((n + 255) / 256);
-  return tiles * 5 >= (long long)(g_dev.sms / 2) * 4;
+  return tiles * 5 >= (long long)(t_ctx->sms / 2) * 4;
 }
 
 #define TC_PLAIN(KIND, OUT, NAME)                                                                     \
@@ -360,22 +420,34 @@ int tc_s8_requant(int m, int n, int k, const void* A, int lda, const void* B, in
 // in split modes are serialised on this buffer by stream order; use one stream per library instance.
 // K extent accumulated inside the tensor core before folding into C (0 = whole K): [0] BF16X3, [1] BF16X2
 int g_split_chunk_k[2] = {512, 1024};
-struct SplitWs { void* p = nullptr; size_t bytes = 0; };
-SplitWs g_split_ws;
-// Starts at 256 MiB (every size of the reference's 256..4096 sweep fits: its harness averages the first,
-// cold call into each row, and a cudaFree + cudaMalloc there costs tens of ms) and at least doubles.
-int split_ws_reserve(size_t need, cudaStream_t st) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (g_split_ws.bytes >= need) return B200_OK;
-  size_t want = g_split_ws.bytes ? 2 * g_split_ws.bytes : ((size_t)256 << 20);
+// Grows the device's split workspace to `need` bytes.  Starts at 256 MiB (every size of the reference's
+// 256..4096 sweep fits: its harness averages the first, cold call into each row, and a cudaFree +
+// cudaMalloc there costs tens of ms) and at least doubles.  Growth synchronises the device (other
+// streams may still read the old buffer); steady-state calls never allocate.  Caller holds ws_mu.
+int split_ws_reserve(size_t need) {
+  DevCtx* c = t_ctx;
+  if (c->ws.bytes >= need) return B200_OK;
+  size_t want = c->ws.bytes ? 2 * c->ws.bytes : ((size_t)256 << 20);
   if (want < need) want = need;
-  if (g_split_ws.p) { cudaStreamSynchronize(st); cudaFree(g_split_ws.p); }
-  g_split_ws.p = nullptr; g_split_ws.bytes = 0;
-  cudaError_t e = cudaMalloc(&g_split_ws.p, want);
-  if (e != cudaSuccess && want > need) { cudaGetLastError(); want = need; e = cudaMalloc(&g_split_ws.p, want); }
-  if (e != cudaSuccess) { cudaGetLastError(); g_split_ws.p = nullptr; return (int)e; }
-  g_split_ws.bytes = want;
+  if (c->ws.p) { cudaDeviceSynchronize(); cudaFree(c->ws.p); }
+  c->ws.p = nullptr; c->ws.bytes = 0; c->ws_busy = false;
+  cudaError_t e = cudaMalloc(&c->ws.p, want);
+  if (e != cudaSuccess && want > need) { cudaGetLastError(); want = need; e = cudaMalloc(&c->ws.p, want); }
+  if (e != cudaSuccess) { cudaGetLastError(); c->ws.p = nullptr; return (int)e; }
+  c->ws.bytes = want;
   return B200_OK;
+}
+// Stream ordering of workspace users: a call on a stream other than the last user's waits (on the device)
+// for that user's GEMM; ws_release records the event the next foreign-stream user will wait on.
+void ws_acquire(cudaStream_t st) {
+  DevCtx* c = t_ctx;
+  if (c->ws_busy && c->ws_stream != st) cudaStreamWaitEvent(st, c->ws_event, 0);
+}
+void ws_release(cudaStream_t st) {
+  DevCtx* c = t_ctx;
+  cudaEventRecord(c->ws_event, st);
+  c->ws_stream = st;
+  c->ws_busy = true;
 }
 
 // Plane geometry shared by the per-call pre-pass and the pre-split B handle (b200_gemm_f32_pack_b).
@@ -388,7 +460,7 @@ int launch_split(const SplitJob& ja, const SplitJob& jb, int jobs, cudaStream_t 
   const long long wide = jobs == 2 && jb.dld > ja.dld ? jb.dld : ja.dld;
   const int tall = jobs == 2 && jb.plane_rows > ja.plane_rows ? jb.plane_rows : ja.plane_rows;
   const int gx = (int)((wide + 2047) / 2048);
-  int gy = (g_dev.sms * 8 + jobs * gx - 1) / (jobs * gx);        // ~8 blocks per SM over the launch
+  int gy = (t_ctx->sms * 8 + jobs * gx - 1) / (jobs * gx);        // ~8 blocks per SM over the launch
   if (gy > (tall + 1) / 2) gy = (tall + 1) / 2;
   if (gy < 1) gy = 1;
   split_planes_kernel<NP><<<dim3(gx, gy, jobs), 256, 0, st>>>(ja, jb);
@@ -404,10 +476,13 @@ int gemm_f32_split(int m, int n, int k, const float* A, int lda, const float* B,
   const int kp = b_plane_rows(k);
   const size_t a_bytes = (size_t)NP * m * pka * 2, b_bytes = (size_t)NP * kp * pnb * 2;
   const size_t a_off = (a_bytes + 1023) & ~(size_t)1023;
-  if (int rc = split_ws_reserve(prepB ? a_off : a_off + b_bytes, st)) return rc;
-  uint16_t* pA = reinterpret_cast<uint16_t*>(g_split_ws.p);
+  std::lock_guard<std::mutex> wlk(t_ctx->ws_mu);
+  if (int rc = split_ws_reserve(prepB ? a_off : a_off + b_bytes)) return rc;
+  ws_acquire(st);
+  struct Release { cudaStream_t s; ~Release() { ws_release(s); } } rel{st};
+  uint16_t* pA = reinterpret_cast<uint16_t*>(t_ctx->ws.p);
   const uint16_t* pB = prepB ? prepB
-                             : reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(g_split_ws.p) + a_off);
+                             : reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(t_ctx->ws.p) + a_off);
   const SplitJob ja{A, lda, m, k, pA, pka, m}, jb{B, ldb, k, n, const_cast<uint16_t*>(pB), pnb, kp};
   int rc = launch_split<NP>(ja, jb, prepB ? 1 : 2, st);
   if (rc) return rc;
@@ -433,41 +508,130 @@ int gemm_f32_split(int m, int n, int k, const float* A, int lda, const float* B,
 
 // B200_F32_F16X2: scaled fp16 split, 3 products.  Row maxima of A and column maxima of B give exact
 // power-of-two scalings that bring every operand into [-1, 1] (fp16 has 5 exponent bits); the
-// epilogue multiplies them back.  Launches: memset, 2 x absmax, 2 x split, GEMM.
-int gemm_f32_split_f16(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                       cudaStream_t st, int acc = 0) {
+// epilogue multiplies them back.  Launches: rows of A (max + scale + split fused), column maxima of B,
+// columns of B, GEMM.
+struct F16Operand {           // one operand as two stacked fp16 planes + the maxima its scaling came from
+  const uint16_t* planes;     // plane p at row p * plane_rows
+  long long pitch;            // elements (multiple of 8)
+  int plane_rows;
+  const float* maxv;          // [rows of A] / [columns of B]
+};
+inline long long f16_pitch(int cols) { return ((long long)cols + 7) & ~7LL; }
+inline int f16_b_rows(int k) { return (k + 31) & ~31; }
+
+// A (rows x cols, scaled by row) -> planes + rmax.  One launch, each row read from HBM once.
+int launch_f16_split_rows(const float* A, long long lda, int rows, int cols, float* rmax, uint16_t* planes,
+                          long long pitch, int plane_rows, cudaStream_t st) {
+  int blocks = (plane_rows + 7) / 8;                       // one warp per row, 8 rows per block
+  const int cap = t_ctx->sms * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (cols <= 1024) split_f16_rows_kernel<4><<<blocks, 256, 0, st>>>(A, lda, rows, cols, rmax, planes, pitch, plane_rows);
+  else if (cols <= 2048) split_f16_rows_kernel<8><<<blocks, 256, 0, st>>>(A, lda, rows, cols, rmax, planes, pitch, plane_rows);
+  else if (cols <= 4096) split_f16_rows_kernel<16><<<blocks, 256, 0, st>>>(A, lda, rows, cols, rmax, planes, pitch, plane_rows);
+  else split_f16_rows_kernel<0><<<blocks, 256, 0, st>>>(A, lda, rows, cols, rmax, planes, pitch, plane_rows);
+  g_launches++;
+  return last_launch_status();
+}
+
+// B (rows x cols, scaled by column) -> planes + cmax (must be zero on entry).  Two launches.  zero_buf:
+// another buffer to clear on the way (the idle half of the double-buffered maxima), or null.
+int launch_f16_split_cols(const float* B, long long ldb, int rows, int cols, float* cmax, uint16_t* planes,
+                          long long pitch, int plane_rows, float* zero_buf, int zero_n, cudaStream_t st) {
+  col_absmax_kernel<<<dim3((cols + 127) / 128, (rows + 127) / 128), 256, 0, st>>>(B, ldb, rows, cols,
+                                                                                  reinterpret_cast<unsigned int*>(cmax));
+  const int gx = (int)((pitch + 2047) / 2048);
+  int gy = (t_ctx->sms * 8 + gx - 1) / gx;
+  if (gy > (plane_rows + 1) / 2) gy = (plane_rows + 1) / 2;
+  if (gy < 1) gy = 1;
+  if (zero_buf && zero_n > gx * 2048) {                    // wider than this launch covers: clear it separately
+    cudaMemsetAsync(zero_buf, 0, (size_t)zero_n * 4, st);
+    zero_buf = nullptr;
+  }
+  split_f16_cols_kernel<<<dim3(gx, gy), 256, 0, st>>>(B, ldb, rows, cols, cmax, planes, pitch, plane_rows, zero_buf, zero_n);
+  g_launches += 2;
+  return last_launch_status();
+}
+
+int gemm_f16x2_core(int m, int n, int k, const F16Operand& a, const F16Operand& b, float* C, int ldc, int acc,
+                    cudaStream_t st) {
   constexpr int NP = 2;
-  const long long pka = ((long long)k + 7) & ~7LL, pnb = ((long long)n + 7) & ~7LL;
-  const int kp = (k + 31) & ~31;
-  const size_t a_bytes = (size_t)NP * m * pka * 2, b_bytes = (size_t)NP * kp * pnb * 2;
-  const size_t a_off = (a_bytes + 1023) & ~(size_t)1023;
-  const size_t b_off = (a_off + b_bytes + 1023) & ~(size_t)1023;       // row maxima, then column maxima
-  const size_t c_off = b_off + (((size_t)m * 4 + 1023) & ~(size_t)1023);
-  const size_t total = c_off + (size_t)n * 4;
-  if (int rc = split_ws_reserve(total, st)) return rc;
-  uint8_t* base = reinterpret_cast<uint8_t*>(g_split_ws.p);
-  uint16_t* pA = reinterpret_cast<uint16_t*>(base);
-  uint16_t* pB = reinterpret_cast<uint16_t*>(base + a_off);
-  float* rmax = reinterpret_cast<float*>(base + b_off);
-  float* cmax = reinterpret_cast<float*>(base + c_off);
-  cudaError_t e = cudaMemsetAsync(cmax, 0, (size_t)n * 4, st);
-  if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
-  const int blocks = g_dev.sms * 8;
-  row_absmax_kernel<<<blocks, 256, 0, st>>>(A, lda, m, k, rmax);
-  col_absmax_kernel<<<dim3((n + 255) / 256, (k + 63) / 64), 256, 0, st>>>(B, ldb, k, n, reinterpret_cast<unsigned int*>(cmax));
-  split_planes_f16_kernel<true><<<blocks, 256, 0, st>>>(A, lda, m, k, rmax, pA, pka, m);
-  split_planes_f16_kernel<false><<<blocks, 256, 0, st>>>(B, ldb, k, n, cmax, pB, pnb, kp);
-  g_launches += 4;
-  int rc = last_launch_status();
-  if (rc) return rc;
   if (use_pair(m, n))
-    return launch_tc<KIND_FP16, 256, 6, float, ProdX2, 64, 2>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st,
-                                                              "tc_f16x2_2cta_256x256", g_split_chunk_k[1], rmax, cmax, acc);
-  if (pick_bn(m, n, true, false) == 256)
-    return launch_tc<KIND_FP16, 256, 4, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st,
-                                                           "tc_f16x2_128x256", g_split_chunk_k[1], rmax, cmax, acc);
-  return launch_tc<KIND_FP16, 128, 6, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st,
-                                                         "tc_f16x2_128x128", g_split_chunk_k[1], rmax, cmax, acc);
+    return launch_tc<KIND_FP16, 256, 6, float, ProdX2, 64, 2>(m, n, k, a.planes, a.pitch, NP * a.plane_rows, a.plane_rows,
+                                                              b.planes, b.pitch, NP * b.plane_rows, b.plane_rows, C, ldc, st,
+                                                              "tc_f16x2_2cta_256x256", g_split_chunk_k[1], a.maxv, b.maxv, acc);
+  const int bn = pick_bn(m, n, true);
+  if (bn == 256)
+    return launch_tc<KIND_FP16, 256, 4, float, ProdX2, 64>(m, n, k, a.planes, a.pitch, NP * a.plane_rows, a.plane_rows,
+                                                           b.planes, b.pitch, NP * b.plane_rows, b.plane_rows, C, ldc, st,
+                                                           "tc_f16x2_128x256", g_split_chunk_k[1], a.maxv, b.maxv, acc);
+  if (bn == 192)
+    return launch_tc<KIND_FP16, 192, 5, float, ProdX2, 64>(m, n, k, a.planes, a.pitch, NP * a.plane_rows, a.plane_rows,
+                                                           b.planes, b.pitch, NP * b.plane_rows, b.plane_rows, C, ldc, st,
+                                                           "tc_f16x2_128x192", g_split_chunk_k[1], a.maxv, b.maxv, acc);
+  return launch_tc<KIND_FP16, 128, 6, float, ProdX2, 64>(m, n, k, a.planes, a.pitch, NP * a.plane_rows, a.plane_rows,
+                                                         b.planes, b.pitch, NP * b.plane_rows, b.plane_rows, C, ldc, st,
+                                                         "tc_f16x2_128x128", g_split_chunk_k[1], a.maxv, b.maxv, acc);
+}
+
+// Column maxima are double-buffered outside the grow-only workspace: call i accumulates into half i % 2
+// (atomicMax needs zeros) and its split launch re-zeroes the other half for call i + 1.
+int cmax_reserve(int n, float** cur, float** other, int* other_dirty) {
+  DevCtx* c = t_ctx;
+  if (c->cmax_cap < (size_t)n) {
+    size_t cap = c->cmax_cap ? 2 * c->cmax_cap : 16384;
+    if (cap < (size_t)n) cap = (size_t)n;
+    if (c->cmax_buf) { cudaDeviceSynchronize(); cudaFree(c->cmax_buf); }
+    c->cmax_buf = nullptr; c->cmax_cap = 0;
+    cudaError_t e = cudaMalloc(&c->cmax_buf, 2 * cap * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(c->cmax_buf, 0, 2 * cap * sizeof(float));
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    c->cmax_cap = cap;
+    c->cmax_dirty[0] = c->cmax_dirty[1] = 0;
+  }
+  const unsigned slot = c->cmax_slot++ & 1u;
+  *cur = c->cmax_buf + slot * c->cmax_cap;
+  *other = c->cmax_buf + (slot ^ 1u) * c->cmax_cap;
+  *other_dirty = c->cmax_dirty[slot ^ 1u];
+  c->cmax_dirty[slot ^ 1u] = 0;
+  c->cmax_dirty[slot] = n;
+  return 0;
+}
+
+// prepA / prepB: operands split earlier (b200_gemm_f32_pack_a / _pack_b), or null = split here.
+int gemm_f32_split_f16(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                       cudaStream_t st, int acc = 0, const F16Operand* prepA = nullptr, const F16Operand* prepB = nullptr) {
+  constexpr int NP = 2;
+  const long long pka = f16_pitch(k), pnb = f16_pitch(n);
+  const int kp = f16_b_rows(k);
+  const size_t a_bytes = prepA ? 0 : (size_t)NP * m * pka * 2, b_bytes = prepB ? 0 : (size_t)NP * kp * pnb * 2;
+  const size_t a_off = (a_bytes + 1023) & ~(size_t)1023;
+  const size_t r_off = (a_off + b_bytes + 1023) & ~(size_t)1023;       // row maxima
+  const size_t total = r_off + (prepA ? 0 : (size_t)m * 4);
+  F16Operand oa, ob;
+  if (prepA && prepB) return gemm_f16x2_core(m, n, k, *prepA, *prepB, C, ldc, acc, st);
+  std::lock_guard<std::mutex> wlk(t_ctx->ws_mu);
+  if (int rc = split_ws_reserve(total)) return rc;
+  ws_acquire(st);
+  struct Release { cudaStream_t s; ~Release() { ws_release(s); } } rel{st};
+  uint8_t* base = reinterpret_cast<uint8_t*>(t_ctx->ws.p);
+  if (prepA) oa = *prepA;
+  else {
+    uint16_t* pA = reinterpret_cast<uint16_t*>(base);
+    float* rmax = reinterpret_cast<float*>(base + r_off);
+    if (int rc = launch_f16_split_rows(A, lda, m, k, rmax, pA, pka, m, st)) return rc;
+    oa = F16Operand{pA, pka, m, rmax};
+  }
+  if (prepB) ob = *prepB;
+  else {
+    uint16_t* pB = reinterpret_cast<uint16_t*>(base + a_off);
+    float *cmax, *other;
+    int other_dirty;
+    if (int rc = cmax_reserve(n, &cmax, &other, &other_dirty)) return rc;
+    if (int rc = launch_f16_split_cols(B, ldb, k, n, cmax, pB, pnb, kp, other, other_dirty, st)) return rc;
+    ob = F16Operand{pB, pnb, kp, cmax};
+  }
+  return gemm_f16x2_core(m, n, k, oa, ob, C, ldc, acc, st);
 }
 
 int launch_ffma(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
@@ -486,17 +650,12 @@ int launch_ffma(int m, int n, int k, const float* A, int lda, const float* B, in
   p.tiles_n = (n + Cfg::BN - 1) / Cfg::BN;
   p.group_m = 8;
   // 2 CTAs per SM: tiles of the last, at most half-full round are issued as two half tiles each
-  const int tiles = p.tiles_m * p.tiles_n, slots = 2 * g_dev.sms;
+  const int tiles = p.tiles_m * p.tiles_n, slots = 2 * t_ctx->sms;
   const int rem = tiles % slots;
   const bool halves = g_ffma_halves && rem > 0 && 2 * rem <= slots;
   p.full_tiles = halves ? tiles - rem : tiles;
   const int ctas = p.full_tiles + 2 * (tiles - p.full_tiles);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_ffma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
-    attr_set = true;
-  }
+  if (int arc = ensure_smem_attr(gemm_ffma_kernel, Cfg::SMEM_BYTES)) return arc;
   g_ktimer.begin(st);
   gemm_ffma_kernel<<<ctas, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
   g_ktimer.end(st);
@@ -521,17 +680,12 @@ int launch_ffma_fat(int m, int n, int k, const float* A, int lda, const float* B
   p.tiles_n = (n + Cfg::BN - 1) / Cfg::BN;
   p.group_m = 8;
   // 1 CTA per SM: tiles of the last, at most half-full round are issued as two half tiles each
-  const int tiles = p.tiles_m * p.tiles_n, slots = g_dev.sms;
+  const int tiles = p.tiles_m * p.tiles_n, slots = t_ctx->sms;
   const int rem = tiles % slots;
   const bool halves = g_ffma_halves && rem > 0 && 2 * rem <= slots;
   p.full_tiles = halves ? tiles - rem : tiles;
   const int ctas = p.full_tiles + 2 * (tiles - p.full_tiles);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_ffma_fat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
-    attr_set = true;
-  }
+  if (int arc = ensure_smem_attr(gemm_ffma_fat_kernel, Cfg::SMEM_BYTES)) return arc;
   g_ktimer.begin(st);
   gemm_ffma_fat_kernel<<<ctas, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
   g_ktimer.end(st);
@@ -549,8 +703,8 @@ int resolve_f32_mode(int mode) {
     int d = g_default_f32_mode.load();
     if (d < 0) {
       const char* e = getenv("B200GEMM_F32_MODE");
-      d = e ? atoi(e) : B200_F32_BF16X3;
-      if (d < 0 || d == B200_F32_AUTO || d > B200_F32_F16X2) d = B200_F32_BF16X3;
+      d = e ? atoi(e) : B200_F32_F16X2;
+      if (d < 0 || d == B200_F32_AUTO || d > B200_F32_F16X2) d = B200_F32_F16X2;
       g_default_f32_mode.store(d);
     }
     return d;
@@ -573,7 +727,7 @@ int gemm_f32_impl(int m, int n, int k, const float* dA, int lda, const float* dB
   // single-launch strict FFMA2 kernel is within 15 % of it (measured, tools/probe_small.py: 9.3 vs 10.6
   // TFLOP/s at 512^3, 2.0 vs 2.0 at 256^3) and bit-exact against the reference oracle.  From 640^3 the
   // tensor-core path pulls away (19.2 vs 15.0; 63.0 vs 41.0 at 1024^3).
-  if (was_auto && mode == B200_F32_BF16X3 && tma && (double)m * n * k <= 2.0e8) mode = B200_F32_STRICT;
+  if (was_auto && (mode == B200_F32_BF16X3 || mode == B200_F32_F16X2) && tma && (double)m * n * k <= 2.0e8) mode = B200_F32_STRICT;
   switch (mode) {
     case B200_F32_STRICT:
       // 128x256 fat-thread tiles once they fill most of the machine (measured at N = 4096 / 3072 / 2048:
@@ -600,7 +754,7 @@ int gemm_f32_impl(int m, int n, int k, const float* dA, int lda, const float* dB
 
 extern "C" {
 
-const char* b200_gemm_version(void) { return "b200gemm 0.1 (sm_100a; tcgen05+TMA; round 1)"; }
+const char* b200_gemm_version(void) { return "b200gemm 0.2 (sm_100a; tcgen05+TMA; round 2)"; }
 
 int b200_gemm_device_ok(void) { return ensure_device(); }
 
@@ -611,6 +765,7 @@ const char* b200_gemm_strerror(int code) {
     case B200_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (there is no CPU fallback)";
     case B200_ERR_UNSUPPORTED: return "mode not supported for these operands";
     case B200_ERR_TENSORMAP: return "cuTensorMapEncodeTiled failed";
+    case B200_ERR_NCCL: return "NCCL failure (b200_nccl_last_error has the text)";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown";
   }
 }
@@ -689,50 +844,125 @@ int b200_gemm_s8s32(int m, int n, int k, const int8_t* dA, int lda, const int8_t
   return tc_s8(m, n, k, dA, lda, dB, ldb, dC, ldc, st);
 }
 
-// ---- pre-split B (the reference's "packAB interface is open" idea, README.md:85, for the split modes) ----
-struct b200_packed_b {
-  int k, n, np, kp;
-  long long pnb;
+// ---- pre-split operands (the reference's "packAB interface is open" idea, README.md:85, for the split modes) ----
+// One handle type for both sides: bf16 planes (BF16X3 / BF16X2, B only) or scaled fp16 planes with the
+// maxima their scaling came from (F16X2, A or B).
+struct b200_packed {
+  int side;            // 0 = A (rows x cols = m x k), 1 = B (k x n)
+  int rows, cols, mode, np, plane_rows;
+  long long pitch;
   uint16_t* planes;
+  float* maxv;         // F16X2 only
+  int dev;
 };
+struct b200_packed_a : b200_packed {};
+struct b200_packed_b : b200_packed {};
+
+static int pack_operand(int side, int rows, int cols, const float* d, int ld, int precision_mode, b200_packed* h,
+                        cudaStream_t st) {
+  if (rows <= 0 || cols <= 0 || !d || ld < cols) return B200_ERR_BAD_ARG;
+  const int mode = resolve_f32_mode(precision_mode);
+  if (mode != B200_F32_F16X2 && (side != 1 || (mode != B200_F32_BF16X3 && mode != B200_F32_BF16X2))) return B200_ERR_UNSUPPORTED;
+  int rc = ensure_device();
+  if (rc) return rc;
+  h->side = side; h->rows = rows; h->cols = cols; h->mode = mode; h->planes = nullptr; h->maxv = nullptr;
+  h->dev = t_ctx->dev;
+  if (mode == B200_F32_F16X2) {
+    h->np = 2;
+    h->pitch = f16_pitch(cols);
+    h->plane_rows = side == 0 ? rows : f16_b_rows(rows);
+    const size_t nmax = side == 0 ? (size_t)rows : (size_t)cols;
+    cudaError_t e = cudaMalloc(&h->planes, (size_t)2 * h->plane_rows * h->pitch * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&h->maxv, nmax * 4);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    if (side == 0) return launch_f16_split_rows(d, ld, rows, cols, h->maxv, h->planes, h->pitch, h->plane_rows, st);
+    e = cudaMemsetAsync(h->maxv, 0, nmax * 4, st);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    return launch_f16_split_cols(d, ld, rows, cols, h->maxv, h->planes, h->pitch, h->plane_rows, nullptr, 0, st);
+  }
+  h->np = mode == B200_F32_BF16X3 ? 3 : 2;
+  h->pitch = plane_pitch(cols);
+  h->plane_rows = b_plane_rows(rows);
+  cudaError_t e = cudaMalloc(&h->planes, (size_t)h->np * h->plane_rows * h->pitch * 2);
+  if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+  const SplitJob jb{d, ld, rows, cols, h->planes, h->pitch, h->plane_rows};
+  return h->np == 3 ? launch_split<3>(jb, jb, 1, st) : launch_split<2>(jb, jb, 1, st);
+}
+static void pack_release(b200_packed* h) {
+  if (!h) return;
+  if (h->planes) cudaFree(h->planes);
+  if (h->maxv) cudaFree(h->maxv);
+}
 
 int b200_gemm_f32_pack_b(int k, int n, const float* dB, int ldb, int precision_mode, b200_packed_b** out,
                          void* stream) {
   if (!out) return B200_ERR_BAD_ARG;
   *out = nullptr;
-  if (k <= 0 || n <= 0 || !dB || ldb < n) return B200_ERR_BAD_ARG;
-  const int mode = resolve_f32_mode(precision_mode);
-  if (mode != B200_F32_BF16X3 && mode != B200_F32_BF16X2) return B200_ERR_UNSUPPORTED;
-  int rc = ensure_device();
-  if (rc) return rc;
-  b200_packed_b* h = new b200_packed_b{k, n, mode == B200_F32_BF16X3 ? 3 : 2, b_plane_rows(k), plane_pitch(n), nullptr};
-  cudaError_t e = cudaMalloc(&h->planes, (size_t)h->np * h->kp * h->pnb * 2);
-  if (e != cudaSuccess) { cudaGetLastError(); delete h; return (int)e; }
-  const SplitJob jb{dB, ldb, k, n, h->planes, h->pnb, h->kp};
-  rc = h->np == 3 ? launch_split<3>(jb, jb, 1, (cudaStream_t)stream) : launch_split<2>(jb, jb, 1, (cudaStream_t)stream);
+  b200_packed_b* h = new b200_packed_b();
+  int rc = pack_operand(1, k, n, dB, ldb, precision_mode, h, (cudaStream_t)stream);
   t_last_kernel = "split_planes";
-  if (rc) { cudaFree(h->planes); delete h; return rc; }
+  if (rc) { pack_release(h); delete h; return rc; }
   *out = h;
   return B200_OK;
 }
 
-int b200_gemm_f32_packed(int m, int n, int k, const float* dA, int lda, const b200_packed_b* pb, float* dC,
-                         int ldc, int accumulate, void* stream) {
-  if (!pb || pb->k != k || pb->n != n) return B200_ERR_BAD_ARG;
-  int rc = check_args(m, n, k, dA, lda, pb->planes, n, dC, ldc);
+int b200_gemm_f32_pack_a(int m, int k, const float* dA, int lda, int precision_mode, b200_packed_a** out,
+                         void* stream) {
+  if (!out) return B200_ERR_BAD_ARG;
+  *out = nullptr;
+  b200_packed_a* h = new b200_packed_a();
+  int rc = pack_operand(0, m, k, dA, lda, precision_mode, h, (cudaStream_t)stream);
+  t_last_kernel = "split_planes";
+  if (rc) { pack_release(h); delete h; return rc; }
+  *out = h;
+  return B200_OK;
+}
+
+// k0: first column of packed A / first row of B this product starts at (K-sliced consumers); the B handle
+// always covers exactly the k rows multiplied.
+static int gemm_packed_impl(int m, int n, int k, const float* dA, int lda, const b200_packed* pa, int a_k0,
+                            const b200_packed* pb, float* dC, int ldc, int accumulate, cudaStream_t st) {
+  if (!pb || pb->rows != k || pb->cols != n) return B200_ERR_BAD_ARG;
+  if (pa && (pa->rows != m || a_k0 < 0 || a_k0 + k > pa->cols || (a_k0 & 7) || pa->mode != pb->mode)) return B200_ERR_BAD_ARG;
+  int rc = check_args(m, n, k, pa ? (const void*)pa->planes : (const void*)dA, pa ? k : lda, pb->planes, n, dC, ldc);
   if (rc == 1) return 0;
   if (rc) return rc;
   rc = ensure_device();
   if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
+  if (pb->dev != t_ctx->dev || (pa && pa->dev != t_ctx->dev)) return B200_ERR_BAD_ARG;
+  if (pb->mode == B200_F32_F16X2) {
+    const F16Operand ob{pb->planes, pb->pitch, pb->plane_rows, pb->maxv};
+    if (pa) {
+      const F16Operand oa{pa->planes + a_k0, pa->pitch, pa->plane_rows, pa->maxv};
+      return gemm_f32_split_f16(m, n, k, nullptr, 0, nullptr, 0, dC, ldc, st, accumulate ? 1 : 0, &oa, &ob);
+    }
+    return gemm_f32_split_f16(m, n, k, dA, lda, nullptr, 0, dC, ldc, st, accumulate ? 1 : 0, nullptr, &ob);
+  }
+  if (pa) return B200_ERR_UNSUPPORTED;
   return pb->np == 3 ? gemm_f32_split<3>(m, n, k, dA, lda, nullptr, 0, dC, ldc, st, accumulate ? 1 : 0, pb->planes)
                      : gemm_f32_split<2>(m, n, k, dA, lda, nullptr, 0, dC, ldc, st, accumulate ? 1 : 0, pb->planes);
 }
 
+int b200_gemm_f32_packed(int m, int n, int k, const float* dA, int lda, const b200_packed_b* pb, float* dC,
+                         int ldc, int accumulate, void* stream) {
+  return gemm_packed_impl(m, n, k, dA, lda, nullptr, 0, pb, dC, ldc, accumulate, (cudaStream_t)stream);
+}
+
+int b200_gemm_f32_packed_ab(int m, int n, int k, const b200_packed_a* pa, int a_k0, const b200_packed_b* pb,
+                            float* dC, int ldc, int accumulate, void* stream) {
+  if (!pa) return B200_ERR_BAD_ARG;
+  return gemm_packed_impl(m, n, k, nullptr, 0, pa, a_k0, pb, dC, ldc, accumulate, (cudaStream_t)stream);
+}
+
 void b200_gemm_f32_pack_free(b200_packed_b* pb) {
   if (!pb) return;
-  if (pb->planes) cudaFree(pb->planes);
+  pack_release(pb);
   delete pb;
+}
+void b200_gemm_f32_pack_free_a(b200_packed_a* pa) {
+  if (!pa) return;
+  pack_release(pa);
+  delete pa;
 }
 
 int b200_gemm_s8s8_requant(int m, int n, int k, const int8_t* dA, int lda, const int8_t* dB, int ldb,
@@ -767,45 +997,21 @@ int b200_convert_f32_to_bf16(const float* dSrc, uint16_t* dDst, size_t count, vo
 // MY_MMult NREPEATS times, aarch64/test_MMult.cpp:105-117) pay no cudaMalloc after the first.
 // Copies are asynchronous on the legacy stream; pinned host buffers run at full PCIe rate.
 namespace {
-struct Scratch { void* p = nullptr; size_t bytes = 0; };
-Scratch g_scr[4];
-std::mutex g_host_mu;
 cudaError_t scratch(int i, size_t bytes, void** out) {
-  if (g_scr[i].bytes < bytes) {
-    if (g_scr[i].p) cudaFree(g_scr[i].p);
-    g_scr[i].p = nullptr; g_scr[i].bytes = 0;
-    cudaError_t e = cudaMalloc(&g_scr[i].p, bytes);
+  Scratch* scr = t_ctx->scr;
+  if (scr[i].bytes < bytes) {
+    if (scr[i].p) cudaFree(scr[i].p);
+    scr[i].p = nullptr; scr[i].bytes = 0;
+    cudaError_t e = cudaMalloc(&scr[i].p, bytes);
     if (e != cudaSuccess) return e;
-    g_scr[i].bytes = bytes;
+    scr[i].bytes = bytes;
   }
-  *out = g_scr[i].p;
+  *out = scr[i].p;
   return cudaSuccess;
 }
 }  // namespace
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cudaGetLastError(); return (int)e_; } } while (0)
-
-// Streams / events of the pipelined host path (created once).
-namespace {
-struct HostPipe {
-  bool ready = false;
-  cudaStream_t h2d = nullptr, comp = nullptr, d2h = nullptr;
-  cudaEvent_t in[8] = {}, done[8] = {};
-  cudaError_t init() {
-    if (ready) return cudaSuccess;
-    cudaError_t e;
-    if ((e = cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking)) != cudaSuccess) return e;
-    if ((e = cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking)) != cudaSuccess) return e;
-    if ((e = cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking)) != cudaSuccess) return e;
-    for (int i = 0; i < 8; i++) {
-      if ((e = cudaEventCreateWithFlags(&in[i], cudaEventDisableTiming)) != cudaSuccess) return e;
-      if ((e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming)) != cudaSuccess) return e;
-    }
-    ready = true;
-    return cudaSuccess;
-  }
-} g_pipe;
-}  // namespace
 
 int b200_gemm_f32_host(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C,
                        int ldc, int precision_mode) {
@@ -814,7 +1020,7 @@ int b200_gemm_f32_host(int m, int n, int k, const float* A, int lda, const float
   if (rc) return rc;
   rc = ensure_device();
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(g_host_mu);
+  std::lock_guard<std::mutex> lk(t_ctx->host_mu);
   float *dA = nullptr, *dB = nullptr, *dC = nullptr;
   const int mode = resolve_f32_mode(precision_mode);
   // device images: pitches rounded up to 4 floats so the TMA paths apply to any k, n
@@ -842,26 +1048,26 @@ int b200_gemm_f32_host(int m, int n, int k, const float* A, int lda, const float
     CK(cudaStreamSynchronize(st));
     return 0;
   }
-  CK(g_pipe.init());
-  CK(cudaMemcpy2DAsync(dB, pb, B, (size_t)ldb * 4, (size_t)n * 4, k, cudaMemcpyHostToDevice, g_pipe.h2d));
+  CK(t_ctx->pipe.init());
+  CK(cudaMemcpy2DAsync(dB, pb, B, (size_t)ldb * 4, (size_t)n * 4, k, cudaMemcpyHostToDevice, t_ctx->pipe.h2d));
   const int rows_per = ((m + blocks - 1) / blocks + 255) & ~255;       // whole 256-row pair tiles per block
   int nb = 0;
   for (int r0 = 0; r0 < m; r0 += rows_per, nb++) {
     const int rows = m - r0 < rows_per ? m - r0 : rows_per;
     float* dAi = dA + (size_t)r0 * pk;
     float* dCi = dC + (size_t)r0 * pn;
-    CK(cudaMemcpy2DAsync(dAi, pa, A + (size_t)r0 * lda, (size_t)lda * 4, (size_t)k * 4, rows, cudaMemcpyHostToDevice, g_pipe.h2d));
-    CK(cudaMemcpy2DAsync(dCi, pc, C + (size_t)r0 * ldc, (size_t)ldc * 4, (size_t)n * 4, rows, cudaMemcpyHostToDevice, g_pipe.h2d));
-    CK(cudaEventRecord(g_pipe.in[nb], g_pipe.h2d));
-    CK(cudaStreamWaitEvent(g_pipe.comp, g_pipe.in[nb], 0));
-    rc = gemm_f32_impl(rows, n, k, dAi, pk, dB, pn, dCi, pn, mode, /*accumulate=*/1, g_pipe.comp);
+    CK(cudaMemcpy2DAsync(dAi, pa, A + (size_t)r0 * lda, (size_t)lda * 4, (size_t)k * 4, rows, cudaMemcpyHostToDevice, t_ctx->pipe.h2d));
+    CK(cudaMemcpy2DAsync(dCi, pc, C + (size_t)r0 * ldc, (size_t)ldc * 4, (size_t)n * 4, rows, cudaMemcpyHostToDevice, t_ctx->pipe.h2d));
+    CK(cudaEventRecord(t_ctx->pipe.in[nb], t_ctx->pipe.h2d));
+    CK(cudaStreamWaitEvent(t_ctx->pipe.comp, t_ctx->pipe.in[nb], 0));
+    rc = gemm_f32_impl(rows, n, k, dAi, pk, dB, pn, dCi, pn, mode, /*accumulate=*/1, t_ctx->pipe.comp);
     if (rc) return rc;
-    CK(cudaEventRecord(g_pipe.done[nb], g_pipe.comp));
-    CK(cudaStreamWaitEvent(g_pipe.d2h, g_pipe.done[nb], 0));
-    CK(cudaMemcpy2DAsync(C + (size_t)r0 * ldc, (size_t)ldc * 4, dCi, pc, (size_t)n * 4, rows, cudaMemcpyDeviceToHost, g_pipe.d2h));
+    CK(cudaEventRecord(t_ctx->pipe.done[nb], t_ctx->pipe.comp));
+    CK(cudaStreamWaitEvent(t_ctx->pipe.d2h, t_ctx->pipe.done[nb], 0));
+    CK(cudaMemcpy2DAsync(C + (size_t)r0 * ldc, (size_t)ldc * 4, dCi, pc, (size_t)n * 4, rows, cudaMemcpyDeviceToHost, t_ctx->pipe.d2h));
   }
-  CK(cudaStreamSynchronize(g_pipe.d2h));
-  CK(cudaStreamSynchronize(g_pipe.comp));
+  CK(cudaStreamSynchronize(t_ctx->pipe.d2h));
+  CK(cudaStreamSynchronize(t_ctx->pipe.comp));
   return 0;
 }
 
@@ -872,7 +1078,7 @@ int b200_gemm_s8s32_host(int m, int n, int k, const int8_t* A, int lda, const in
   if (rc) return rc;
   rc = ensure_device();
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(g_host_mu);
+  std::lock_guard<std::mutex> lk(t_ctx->host_mu);
   int8_t *dA = nullptr, *dB = nullptr;
   int32_t* dC = nullptr;
   // device images padded to 16-byte pitches so the tcgen05 path is taken for any m,n,k
@@ -894,3 +1100,5 @@ int b200_gemm_s8s32_host(int m, int n, int k, const int8_t* A, int lda, const in
 }
 
 }  // extern "C"
+
+#include "rowpanel.cuh"

@@ -130,9 +130,9 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
   nb = r / rows;
 }
 
-// 2^e (inverse = false) or 2^-e (inverse = true) with e such that maxv * 2^-e lies in [0.5, 1);
-// 1 for zero, denormal, inf or NaN maxima; |e| clamped so both factors stay normal.
-__host__ __device__ __forceinline__ float pow2_factor(float maxv, bool inverse) {
+// Scaled split mode (B200_F32_F16X2): exponent e with maxv * 2^-e in [0.5, 1); 0 for zero, denormal,
+// inf or NaN maxima.  Range [-125, 128].
+__host__ __device__ __forceinline__ int pow2_exp(float maxv) {
   uint32_t bits;
 #ifdef __CUDA_ARCH__
   bits = __float_as_uint(maxv);
@@ -140,14 +140,15 @@ __host__ __device__ __forceinline__ float pow2_factor(float maxv, bool inverse) 
   memcpy(&bits, &maxv, 4);
 #endif
   const int ef = (int)((bits >> 23) & 0xFF);
-  int e = (ef == 0 || ef == 255) ? 0 : ef - 126;
-  e = e > 96 ? 96 : (e < -96 ? -96 : e);
-  const uint32_t out = (uint32_t)(127 + (inverse ? -e : e)) << 23;
-#ifdef __CUDA_ARCH__
-  return __uint_as_float(out);
-#else
-  float f; memcpy(&f, &out, 4); return f;
-#endif
+  return (ef == 0 || ef == 255) ? 0 : ef - 126;
+}
+// 2^e as a float, e in [-126, 127]
+__device__ __forceinline__ float exp2i(int e) { return __uint_as_float((uint32_t)(127 + e) << 23); }
+// x * 2^e for any e in [-256, 256] through two normal power-of-two factors (exact unless the result
+// itself leaves the fp32 range)
+__device__ __forceinline__ float mul_pow2(float x, int e) {
+  const int h = e >> 1;
+  return x * exp2i(h) * exp2i(min(e - h, 127));
 }
 
 struct WorkItem { int tile, part, kb0, kb1, nsub, bn; };
@@ -497,12 +498,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
         // staging -> global: 8 lanes cover one 128-byte row segment, 4 rows per instruction
-        float cs[4] = {1.f, 1.f, 1.f, 1.f};
+        int ce[4] = {0, 0, 0, 0};
         if constexpr (std::is_same<OutT, float>::value) {
           if (p.col_max != nullptr) {
 #pragma unroll
             for (int e = 0; e < 4; e++)
-              if (col + e < p.N) cs[e] = pow2_factor(__ldg(p.col_max + col + e), false);
+              if (col + e < p.N) ce[e] = pow2_exp(__ldg(p.col_max + col + e));
           }
         }
 #pragma unroll
@@ -512,11 +513,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint4 v = *reinterpret_cast<const uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4));
           if constexpr (std::is_same<OutT, float>::value) {
             if (p.row_max != nullptr && gm < p.M) {      // undo the operand scaling: exact powers of two
-              const float rs = pow2_factor(__ldg(p.row_max + gm), false);
-              v.x = __float_as_uint(__uint_as_float(v.x) * (rs * cs[0]));
-              v.y = __float_as_uint(__uint_as_float(v.y) * (rs * cs[1]));
-              v.z = __float_as_uint(__uint_as_float(v.z) * (rs * cs[2]));
-              v.w = __float_as_uint(__uint_as_float(v.w) * (rs * cs[3]));
+              const int re = pow2_exp(__ldg(p.row_max + gm));
+              v.x = __float_as_uint(mul_pow2(__uint_as_float(v.x), re + ce[0]));
+              v.y = __float_as_uint(mul_pow2(__uint_as_float(v.y), re + ce[1]));
+              v.z = __float_as_uint(mul_pow2(__uint_as_float(v.z), re + ce[2]));
+              v.w = __float_as_uint(mul_pow2(__uint_as_float(v.w), re + ce[3]));
             }
           }
           if (gm < p.M) {
@@ -649,61 +650,210 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const SplitJob ja, co
 
 
 // ---- scaled fp16 split (B200_F32_F16X2) ------------------------------------------------------------
-// x' = x * 2^-e (e from the row maximum of A / the column maximum of B, so |x'| <= 1), then
+// x' = x * 2^-e (e from the row maximum of A / the column maximum of B, so |x'| < 1), then
 // x' = h1 + h2 with h1 = fp16(x'), h2 = fp16(x' - h1): 22 significant bits; h2 may be an fp16
-// subnormal (absolute quantum 2^-24 relative to the row/column scale).
-__global__ void row_absmax_kernel(const float* __restrict__ src, long long ld, int rows, int cols,
-                                  float* __restrict__ out) {
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
-    const float* s = src + (long long)r * ld;
-    float mx = 0.f;
-    for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, fabsf(s[c]));
+// subnormal (absolute quantum 2^-24 relative to the row/column scale).  Three launches per GEMM:
+// rows of A (maximum, scaling and split fused: each row is read from HBM once), column maxima of B,
+// columns of B.  All HBM-bound: 4 bytes read + 4 bytes written per element (+ 4 read for B's maxima,
+// mostly L2 hits on the second touch).
+__device__ __forceinline__ void split_f16x8(const float (&x)[8], uint4& h1, uint4& h2) {
+  uint32_t a[4], b[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) out[r] = mx;
+  for (int e = 0; e < 4; e++) {
+    const __half2 p = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
+    const float2 pf = __half22float2(p);
+    const __half2 q = __floats2half2_rn(x[2 * e] - pf.x, x[2 * e + 1] - pf.y);
+    a[e] = *reinterpret_cast<const uint32_t*>(&p);
+    b[e] = *reinterpret_cast<const uint32_t*>(&q);
+  }
+  h1 = make_uint4(a[0], a[1], a[2], a[3]);
+  h2 = make_uint4(b[0], b[1], b[2], b[3]);
+}
+__device__ __forceinline__ void load8(const float* __restrict__ s, int c, int cols, bool vec, float (&x)[8]) {
+  if (vec && c + 8 <= cols) {
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(s + c));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(s + c) + 1);
+    x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+    x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = c + e < cols ? __ldg(s + c + e) : 0.f;
   }
 }
-// out must be zeroed; non-negative floats order like their bit patterns, so atomicMax on uint works
-__global__ void col_absmax_kernel(const float* __restrict__ src, long long ld, int rows, int cols,
-                                  unsigned int* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  const int r0 = blockIdx.y * 64, r1 = min(r0 + 64, rows);
-  float mx = 0.f;
-  for (int r = r0; r < r1; r++) mx = fmaxf(mx, fabsf(src[(long long)r * ld + c]));
-  atomicMax(out + c, __float_as_uint(mx));
+
+// A side: one warp per row.  VPL > 0: the row (cols <= 256 * VPL) stays in registers between the
+// maximum and the split; VPL == 0: any length, second pass re-reads the row (L1 / L2 hits).
+// dst: 2 planes stacked along rows (plane p at row p * plane_rows), pitch dld (multiple of 8); columns
+// [cols, dld) and rows [rows, plane_rows) are written as zero.
+template <int VPL>
+__global__ void __launch_bounds__(256) split_f16_rows_kernel(const float* __restrict__ src, long long ld, int rows,
+                                                             int cols, float* __restrict__ rmax,
+                                                             uint16_t* __restrict__ dst, long long dld, int plane_rows) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < plane_rows; r += nwarps) {
+    uint16_t* d1 = dst + (long long)r * dld;
+    uint16_t* d2 = dst + ((long long)plane_rows + r) * dld;
+    if (r >= rows) {
+      for (int c = lane * 8; c < dld; c += 256) {
+        *reinterpret_cast<uint4*>(d1 + c) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(d2 + c) = make_uint4(0, 0, 0, 0);
+      }
+      continue;
+    }
+    const float* s = src + (long long)r * ld;
+    float mx = 0.f;
+    if constexpr (VPL > 0) {
+      float x[VPL][8];
+#pragma unroll
+      for (int j = 0; j < VPL; j++) {
+        const int c = (j * 32 + lane) * 8;
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[j][e] = 0.f;
+        if (c < cols) load8(s, c, cols, vec, x[j]);
+#pragma unroll
+        for (int e = 0; e < 8; e++) mx = fmaxf(mx, fabsf(x[j][e]));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0) rmax[r] = mx;
+      const int ex = -pow2_exp(mx);
+#pragma unroll
+      for (int j = 0; j < VPL; j++) {
+        const int c = (j * 32 + lane) * 8;
+        if (c < dld) {
+#pragma unroll
+          for (int e = 0; e < 8; e++) x[j][e] = mul_pow2(x[j][e], ex);
+          uint4 h1, h2;
+          split_f16x8(x[j], h1, h2);
+          *reinterpret_cast<uint4*>(d1 + c) = h1;
+          *reinterpret_cast<uint4*>(d2 + c) = h2;
+        }
+      }
+    } else {
+      for (int c0 = lane * 8; c0 < cols; c0 += 1024) {       // 4 vectors in flight per lane
+        float x[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int c = c0 + u * 256;
+#pragma unroll
+          for (int e = 0; e < 8; e++) x[u][e] = 0.f;
+          if (c < cols) load8(s, c, cols, vec, x[u]);
+#pragma unroll
+          for (int e = 0; e < 8; e++) mx = fmaxf(mx, fabsf(x[u][e]));
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0) rmax[r] = mx;
+      const int ex = -pow2_exp(mx);
+      for (int c0 = lane * 8; c0 < dld; c0 += 512) {
+        float x[2][8];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const int c = c0 + u * 256;
+#pragma unroll
+          for (int e = 0; e < 8; e++) x[u][e] = 0.f;
+          if (c < cols) load8(s, c, cols, vec, x[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const int c = c0 + u * 256;
+          if (c < dld) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) x[u][e] = mul_pow2(x[u][e], ex);
+            uint4 h1, h2;
+            split_f16x8(x[u], h1, h2);
+            *reinterpret_cast<uint4*>(d1 + c) = h1;
+            *reinterpret_cast<uint4*>(d2 + c) = h2;
+          }
+        }
+      }
+    }
+  }
 }
-template <bool BY_ROW>
-__global__ void split_planes_f16_kernel(const float* __restrict__ src, long long ld, int rows, int cols,
-                                        const float* __restrict__ maxv, uint16_t* __restrict__ dst,
-                                        long long dld, int plane_rows) {
-  const int cgroups = (int)(dld >> 2);
-  const long long total = (long long)plane_rows * cgroups;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(i / cgroups);
-    const int c = (int)(i - (long long)r * cgroups) * 4;
-    float x[4] = {0.f, 0.f, 0.f, 0.f};
-    if (r < rows) {
-      const float rowf = BY_ROW ? pow2_factor(maxv[r], true) : 1.f;
-#pragma unroll
-      for (int e = 0; e < 4; e++)
-        if (c + e < cols) x[e] = src[(long long)r * ld + c + e] * (BY_ROW ? rowf : pow2_factor(maxv[c + e], true));
+
+// Column maxima of B into out[cols] (zero on entry; non-negative floats order like their bit patterns,
+// so atomicMax on the uint view works).  Block: 8 warps over 128 columns x ROWS rows; lane = 4 columns.
+__global__ void __launch_bounds__(256) col_absmax_kernel(const float* __restrict__ src, long long ld, int rows,
+                                                         int cols, unsigned int* __restrict__ out) {
+  constexpr int ROWS = 128;
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + lane * 4;
+  const int r0 = blockIdx.y * ROWS, r1 = min(r0 + ROWS, rows);
+  const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && c + 4 <= cols;
+  float4 mx = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < cols) {
+#pragma unroll 4
+    for (int r = r0 + w; r < r1; r += 8) {
+      const float* s = src + (long long)r * ld + c;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vec) v = __ldg(reinterpret_cast<const float4*>(s));
+      else {
+        v.x = s[0];
+        if (c + 1 < cols) v.y = s[1];
+        if (c + 2 < cols) v.z = s[2];
+        if (c + 3 < cols) v.w = s[3];
+      }
+      mx.x = fmaxf(mx.x, fabsf(v.x)); mx.y = fmaxf(mx.y, fabsf(v.y));
+      mx.z = fmaxf(mx.z, fabsf(v.z)); mx.w = fmaxf(mx.w, fabsf(v.w));
     }
-    uint16_t h1[4], h2[4];
+  }
+  red[w][lane] = mx;
+  __syncthreads();
+  if (w == 0 && c < cols) {
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-      const __half a = __float2half_rn(x[e]);
-      const __half b = __float2half_rn(x[e] - __half2float(a));
-      h1[e] = __half_as_ushort(a);
-      h2[e] = __half_as_ushort(b);
+    for (int i = 1; i < 8; i++) {
+      const float4 o = red[i][lane];
+      mx.x = fmaxf(mx.x, o.x); mx.y = fmaxf(mx.y, o.y); mx.z = fmaxf(mx.z, o.z); mx.w = fmaxf(mx.w, o.w);
     }
-    *reinterpret_cast<uint2*>(dst + (long long)r * dld + c) =
-        make_uint2((uint32_t)h1[0] | ((uint32_t)h1[1] << 16), (uint32_t)h1[2] | ((uint32_t)h1[3] << 16));
-    *reinterpret_cast<uint2*>(dst + ((long long)plane_rows + r) * dld + c) =
-        make_uint2((uint32_t)h2[0] | ((uint32_t)h2[1] << 16), (uint32_t)h2[2] | ((uint32_t)h2[3] << 16));
+    atomicMax(out + c, __float_as_uint(mx.x));
+    if (c + 1 < cols) atomicMax(out + c + 1, __float_as_uint(mx.y));
+    if (c + 2 < cols) atomicMax(out + c + 2, __float_as_uint(mx.z));
+    if (c + 3 < cols) atomicMax(out + c + 3, __float_as_uint(mx.w));
+  }
+}
+
+// B side: a thread owns 8 consecutive columns (their scale exponents live in registers) and walks rows
+// blockIdx.y, +gridDim.y, ... two at a time.  Also re-zeroes `zero_buf` (the idle half of the double-
+// buffered column maxima) for the next call.
+__global__ void __launch_bounds__(256) split_f16_cols_kernel(const float* __restrict__ src, long long ld, int rows,
+                                                             int cols, const float* __restrict__ cmax,
+                                                             uint16_t* __restrict__ dst, long long dld, int plane_rows,
+                                                             float* __restrict__ zero_buf, int zero_n) {
+  const int c = (int)(blockIdx.x * 256 + threadIdx.x) * 8;
+  if (blockIdx.y == 0 && zero_buf != nullptr) {
+#pragma unroll
+    for (int e = 0; e < 8; e++)
+      if (c + e < zero_n) zero_buf[c + e] = 0.f;
+  }
+  if (c >= dld) return;
+  const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  int ex[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) ex[e] = c + e < cols ? -pow2_exp(__ldg(cmax + c + e)) : 0;
+  for (int r0 = blockIdx.y * 2; r0 < plane_rows; r0 += gridDim.y * 2) {
+    float x[2][8];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int r = r0 + u;
+#pragma unroll
+      for (int e = 0; e < 8; e++) x[u][e] = 0.f;
+      if (r < rows) load8(src + (long long)r * ld, c, cols, vec, x[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int r = r0 + u;
+      if (r >= plane_rows) break;
+#pragma unroll
+      for (int e = 0; e < 8; e++) x[u][e] = mul_pow2(x[u][e], ex[e]);
+      uint4 h1, h2;
+      split_f16x8(x[u], h1, h2);
+      *reinterpret_cast<uint4*>(dst + (long long)r * dld + c) = h1;
+      *reinterpret_cast<uint4*>(dst + ((long long)plane_rows + r) * dld + c) = h2;
+    }
   }
 }
 

@@ -48,6 +48,7 @@ extern "C" {
 #define B200_ERR_NO_DEVICE     -2   /* no sm_100 device / driver entry point missing */
 #define B200_ERR_UNSUPPORTED   -3   /* mode not available for this dtype */
 #define B200_ERR_TENSORMAP     -4   /* cuTensorMapEncodeTiled rejected the operand */
+#define B200_ERR_NCCL          -5   /* libnccl missing or an NCCL call failed: b200_nccl_last_error() */
 
 /* ---- fp32 precision modes (the SURVEY §7 H1 decision, made explicit) ------ */
 enum b200_f32_mode {
@@ -58,9 +59,9 @@ enum b200_f32_mode {
   B200_F32_BF16X3 = 2,   /* split-bf16: a=a1+a2+a3, 6 tcgen05 kind::f16 products per
                             k-step, two-level accumulation (K chunks of 512 folded
                             into C with rounded fp32 adds): fp32-class error on the
-                            tensor cores.  THE LIBRARY DEFAULT.                    */
+                            tensor cores, elementwise.  The round-1 default.      */
   B200_F32_BF16X2 = 3,   /* split-bf16: a=a1+a2, 3 products, ~2^-17 relative       */
-  B200_F32_AUTO   = 4,   /* library default: BF16X3 unless the environment variable
+  B200_F32_AUTO   = 4,   /* library default: F16X2 unless the environment variable
                             B200GEMM_F32_MODE or b200_gemm_set_default_f32_mode
                             says otherwise; problems up to ~512^3 with TMA-able
                             operands take the single-launch STRICT kernel          */
@@ -69,7 +70,9 @@ enum b200_f32_mode {
                             bits), 3 tcgen05 kind::f16 products, two-level
                             accumulation, epilogue unscales.  fp32-class NORMWISE
                             error (elements far below their row/column maximum keep
-                            absolute, not relative, precision)                     */
+                            absolute, not relative, precision): half the tensor-core
+                            work of BF16X3 at the same measured error.
+                            THE LIBRARY DEFAULT.                                   */
 };
 
 /* ---- bf16 output selector -------------------------------------------------- */
@@ -131,22 +134,36 @@ int b200_gemm_s8s32_host(int m, int n, int k,
                          const int8_t* A, int lda, const int8_t* B, int ldb,
                          int32_t* C, int ldc);
 
-/* Pre-split B for the split-precision modes (BF16X3 / BF16X2; AUTO = the library default): the
- * reference leaves its "packAB interface open" for callers that reuse one operand (README.md:85;
- * PackMatrixB, aarch64/MMult_4x4_13.cpp:361).  TMA needs no repacking of row-major B, but the fp32 ->
- * bf16-plane split of B is per-call work (half of the pre-pass) that a constant B can pay once.
- * b200_gemm_f32_pack_b splits the k x n matrix into a handle that owns its device memory;
- * b200_gemm_f32_packed computes C = A*B (accumulate = 0) or C += A*B (1) with it and is bit-identical
- * to b200_gemm_f32 / b200_gemm_f32_acc in the handle's mode.  DEVICE pointers; the handle may be used
- * by any number of later calls (stream-ordered after the pack call) and is released with
- * b200_gemm_f32_pack_free.  Modes without a split (STRICT, TF32, F16X2) return B200_ERR_UNSUPPORTED. */
+/* Pre-split operands for the split-precision modes (AUTO = the library default): the reference
+ * leaves its "packAB interface open" for callers that reuse one operand (README.md:85; PackMatrixA/B,
+ * aarch64/MMult_4x4_13.cpp:259,361).  TMA needs no repacking of row-major operands, but the fp32 ->
+ * plane split is per-call work (the pre-pass) that a constant operand can pay once.
+ *   b200_gemm_f32_pack_b   splits the k x n matrix B (F16X2, BF16X3, BF16X2) into a handle that owns its
+ *                          device memory;
+ *   b200_gemm_f32_pack_a   does the same for the m x k matrix A (F16X2 only);
+ *   b200_gemm_f32_packed   computes C = A*B (accumulate = 0) or C += A*B (1) from fp32 A and packed B and
+ *                          is bit-identical to b200_gemm_f32 / b200_gemm_f32_acc in the handle's mode;
+ *   b200_gemm_f32_packed_ab  uses both handles and multiplies columns [a_k0, a_k0 + k) of packed A
+ *                          (a_k0 a multiple of 8) by a packed B of exactly k rows: a K-sliced consumer
+ *                          (B arriving in row blocks over NVLink) splits A once and each block of B as
+ *                          it lands.
+ * DEVICE pointers; a handle may be used by any number of later calls (stream-ordered after the pack
+ * call) on the device it was made on and is released with b200_gemm_f32_pack_free / _free_a.  Modes
+ * without a split (STRICT, TF32) return B200_ERR_UNSUPPORTED. */
 typedef struct b200_packed_b b200_packed_b;
+typedef struct b200_packed_a b200_packed_a;
 int b200_gemm_f32_pack_b(int k, int n, const float* dB, int ldb, int precision_mode,
                          b200_packed_b** out, void* stream);
+int b200_gemm_f32_pack_a(int m, int k, const float* dA, int lda, int precision_mode,
+                         b200_packed_a** out, void* stream);
 int b200_gemm_f32_packed(int m, int n, int k, const float* dA, int lda,
                          const b200_packed_b* packedB, float* dC, int ldc,
                          int accumulate, void* stream);
+int b200_gemm_f32_packed_ab(int m, int n, int k, const b200_packed_a* packedA, int a_k0,
+                            const b200_packed_b* packedB, float* dC, int ldc,
+                            int accumulate, void* stream);
 void b200_gemm_f32_pack_free(b200_packed_b* packedB);
+void b200_gemm_f32_pack_free_a(b200_packed_a* packedA);
 
 /* int8 x int8 -> int8 with the requantising tail of chgemm's kernels fused into the
  * GEMM epilogue (aarch64-int8/int8kernel_m4.S:386-426; signature :40):
@@ -159,6 +176,45 @@ int b200_gemm_s8s8_requant(int m, int n, int k,
                            const int8_t* dA, int lda, const int8_t* dB, int ldb,
                            int8_t* dC, int ldc, const float* dScales,
                            const float* dBias, void* stream);
+
+/* ---- multi-GPU: C sharded by row panels, one exchange step (BASELINE config 5) ------------
+ * The reference has no multi-GPU code; north_star asks for "row-panels across the box's GPUs with one
+ * NCCL broadcast of B over NVLink" behind this C ABI.  One process (or host thread) per GPU; rank i owns
+ * A_i (m_local x k) and C_i (m_local x n); B (k x n) is valid on `root` before the call and on every rank
+ * after it.  B crosses NVLink as K-slices (contiguous row blocks of the row-major operand, broadcast in
+ * place with ncclBroadcast on the plan's own stream); A_i is split into its planes while the first slice
+ * travels and slice j is multiplied while slices j+1.. are in flight.  Timing convention of the
+ * reference's harness: operands resident, the exchange inside the call (cuda/test_MMult.cpp:84-112).
+ *
+ * NCCL is resolved with dlopen at first use (the libnccl.so.2 already loaded in the process, e.g. torch's,
+ * else the system one; b200_nccl_load(path) forces one): libb200gemm.so itself does not link NCCL.
+ *   nccl_comm   an ncclComm_t (as void*): the caller's own (torch: ProcessGroupNCCL._comm_ptr()) or one
+ *               made with b200_comm_unique_id + b200_comm_init_rank (rank 0 creates the 128-byte id and
+ *               hands it to the other ranks by whatever means the host has).  NULL = single rank.
+ *   slice_rows  rows of B per K-slice (sum k, every boundary a multiple of 8), or NULL / n_slices 0 for the
+ *               default (one slice on one rank, else three slices weighted 1:3:4).
+ * The plan owns all scratch (planes, events, streams): the compute calls never allocate. */
+typedef struct b200_rowpanel b200_rowpanel;
+int  b200_nccl_load(const char* libnccl_path_or_null);
+const char* b200_nccl_last_error(void);
+int  b200_comm_unique_id(void* id128);
+int  b200_comm_init_rank(void** nccl_comm_out, const void* id128, int rank, int world);
+int  b200_comm_destroy(void* nccl_comm);
+int  b200_rowpanel_create(b200_rowpanel** out, void* nccl_comm, int m_local_max, int n, int k,
+                          int precision_mode, const int* slice_rows, int n_slices);
+void b200_rowpanel_destroy(b200_rowpanel* plan);
+/* K-slice boundaries of the plan: writes min(n_slices + 1, cap) row offsets, returns n_slices. */
+int  b200_rowpanel_slices(const b200_rowpanel* plan, int* bounds, int cap);
+/* C_local = A_local * B on DEVICE pointers (dB: the operand on root, the receive buffer elsewhere; ldb == n
+ * unless single-rank).  Asynchronous on `stream`. */
+int  b200_gemm_f32_rowpanel(b200_rowpanel* plan, int m_local, int n, int k,
+                            const float* dA_local, int lda, float* dB, int ldb,
+                            float* dC_local, int ldc, int root, void* stream);
+/* C_local += A_local * B with HOST pointers (the 9-arg MY_MMult contract, aarch64/MMult0.cpp:3-23, sharded):
+ * B is read on root only; H2D, exchange, math and D2H are pipelined inside; synchronous. */
+int  b200_gemm_f32_rowpanel_host(b200_rowpanel* plan, int m_local, int n, int k,
+                                 const float* A_local, int lda, const float* B, int ldb,
+                                 float* C_local, int ldc, int root);
 
 /* Element-wise helper the bf16 config needs on the device: round-to-nearest-
  * even fp32 -> bf16 (the rounding SURVEY §8d prescribes for config 3 inputs). */

@@ -116,12 +116,12 @@ def test_f32_split_bf16_modes(gemm, oracle, m, n, k, mode, tol):
 
 def test_f32_split_unaligned_and_default(gemm, oracle):
     """The split pre-pass reads fp32 through plain loads, so odd leading dimensions still take the
-    tensor-core path; AUTO resolves to BF16X3 (include/b200gemm.h)."""
+    tensor-core path; AUTO resolves to F16X2 (include/b200gemm.h)."""
     m, n, k = 200, 136, 264
     A = cuda(_libs.gen_f32(oracle, m, k + 3, 1))[:, :k]
     B = cuda(_libs.gen_f32(oracle, k, n + 5, 2))[:, :n]
     Cbuf = torch.full((m, n + 7), -7.0, device="cuda")
-    assert gemm.lib.b200_gemm_default_f32_mode() == gemm.F32_BF16X3 or os.environ.get("B200GEMM_F32_MODE")
+    assert gemm.lib.b200_gemm_default_f32_mode() == gemm.F32_F16X2 or os.environ.get("B200GEMM_F32_MODE")
     gemm.gemm_f32(A, B, out=Cbuf[:, :n], mode=gemm.F32_BF16X3)
     assert gemm.last_kernel().startswith("tc_bf16x3")
     t = _libs.ref_f64(oracle, A.cpu().numpy(), B.cpu().numpy())

@@ -42,7 +42,7 @@ def _worker(rank, world, port, M, N, K, panel, out_dir):
     A = torch.from_numpy(L.gen_f32(o, M, K, 100))
     B = torch.from_numpy(L.gen_f32(o, K, N, 200)) if rank == 0 else torch.full((K, N), float("nan"))
     r0, r1 = rowpanel.row_panel(rank, world, M)
-    rp = rowpanel.RowPanelGemm(host_gemm, dist, rank, world, K, N, panel, torch.device("cpu"), torch.float32)
+    rp = rowpanel.RowPanelGemm(host_gemm, dist, rank, world, K, N, panel)
     C = torch.full((r1 - r0, N), float("nan"))
     rp.run(A[r0:r1], B, C)
     np.save(os.path.join(out_dir, f"c_{rank}.npy"), C.numpy())
@@ -59,7 +59,7 @@ def test_rowpanel_world2(tmp_path, oracle, M, N, K, panel):
     assert np.array_equal(C, _libs.ref_f32_fma(oracle, a, b))
 
 
-@pytest.mark.parametrize("world,M,N,K,panel", [(4, 41, 24, 200, (1, 3, 4)), (3, 10, 16, 130, 2)])
+@pytest.mark.parametrize("world,M,N,K,panel", [(4, 41, 24, 200, (1, 3, 4)), (3, 10, 16, 130, 2), (2, 33, 40, 1100, None)])
 def test_rowpanel_world_gt2(tmp_path, oracle, world, M, N, K, panel):
     """More ranks than the GPU validation had (the driver's scaling run goes to 8), weighted K-slices."""
     mp.spawn(_worker, args=(world, _free_port(), M, N, K, panel, str(tmp_path)), nprocs=world, join=True)
@@ -84,6 +84,12 @@ def test_partition_helpers():
     assert rowpanel.row_chunks(2, 8) == [(0, 1), (1, 2)]
     assert rowpanel.row_chunks(4096, (1, 3, 4)) == [(0, 512), (512, 2048), (2048, 4096)]
     assert rowpanel.row_chunks(200, (1, 3, 4)) == [(0, 128), (128, 200)]        # 25 rows round to no block
+    # the C++ plan's default schedule (b200_rowpanel_create), mirrored by default_slices
+    assert rowpanel.default_slices(4096, 1) == [(0, 4096)]
+    assert rowpanel.default_slices(4096, 2) == [(0, 512), (512, 2048), (2048, 4096)]
+    assert rowpanel.default_slices(16384, 8) == [(0, 2048), (2048, 8192), (8192, 16384)]
+    assert rowpanel.default_slices(1000, 4) == [(0, 1000)]
+    assert rowpanel.default_slices(1100, 2) == [(0, 192), (192, 576), (576, 1100)]
     for K in (1, 63, 64, 200, 4096, 16384):
         for w in ((1, 3, 4), (1, 1), (5,), (1, 2, 2, 3)):
             ch = rowpanel.row_chunks(K, w)
