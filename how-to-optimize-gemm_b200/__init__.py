@@ -22,7 +22,7 @@ OUT_F32, OUT_BF16 = 0, 1
 EXPORTS = [
     "b200_gemm_version", "b200_gemm_device_ok", "b200_gemm_strerror", "b200_gemm_last_kernel",
     "b200_gemm_launch_count", "b200_gemm_default_f32_mode", "b200_gemm_set_default_f32_mode",
-    "b200_gemm_f32", "b200_gemm_f32_acc", "b200_gemm_f32_host", "b200_gemm_bf16", "b200_gemm_s8s32",
+    "b200_gemm_f32", "b200_gemm_f32_acc", "b200_gemm_f32_ex", "b200_gemm_f32_host", "b200_gemm_bf16", "b200_gemm_s8s32",
     "b200_gemm_s8s32_host", "b200_gemm_s8s8_requant", "b200_gemm_f32_pack_b", "b200_gemm_f32_packed",
     "b200_gemm_f32_pack_free", "b200_nccl_load", "b200_nccl_last_error", "b200_comm_unique_id", "b200_comm_init_rank",
     "b200_comm_destroy", "b200_rowpanel_create", "b200_rowpanel_destroy", "b200_rowpanel_slices", "b200_gemm_f32_rowpanel",
@@ -54,6 +54,7 @@ lib.b200_gemm_last_kernel.restype = C.c_char_p
 lib.b200_gemm_launch_count.restype = C.c_ulonglong
 lib.b200_gemm_f32.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp]
 lib.b200_gemm_f32_acc.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp]
+lib.b200_gemm_f32_ex.argtypes = [_i, _i, _i, C.c_float, _vp, _i, _vp, _i, C.c_float, _vp, _i, _i, _vp]
 lib.b200_gemm_f32_host.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i]
 lib.b200_gemm_bf16.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp]
 lib.b200_gemm_s8s32.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]
@@ -158,6 +159,15 @@ def gemm_f32(A, B, out=None, mode=F32_AUTO, stream=None, accumulate=False):
     fn = lib.b200_gemm_f32_acc if accumulate else lib.b200_gemm_f32
     assert not accumulate or out is not None
     _check(fn(m, n, k, A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), mode, _stream_ptr(stream)))
+    return out
+
+
+def gemm_f32_ex(alpha, A, B, beta, out, mode=F32_AUTO, stream=None):
+    """out = alpha * A*B + beta * out (b200_gemm_f32_ex; cuBLAS sgemm semantics, cuda/MMult_cuBLAS_1.cpp:11-19)."""
+    m, k = A.shape
+    n = B.shape[1]
+    _check(lib.b200_gemm_f32_ex(m, n, k, alpha, A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), beta, out.data_ptr(), _ld(out),
+                                mode, _stream_ptr(stream)))
     return out
 
 

@@ -47,6 +47,9 @@ struct KernelTimer {
 } g_ktimer;
 std::atomic<int> g_default_f32_mode{-1};
 thread_local const char* t_last_kernel = "none";
+// General epilogue request of the current call (b200_gemm_f32_ex): read by launch_tc, reset by the entry point.
+struct EpiOpts { int axpby = 0; float alpha = 1.f, beta = 0.f; };
+thread_local EpiOpts t_epi;
 int g_dbg_b_lbo = 0, g_dbg_b_sbo = 0;
 
 // ---- per-device state ------------------------------------------------------------------------------
@@ -249,16 +252,17 @@ int launch_generic_requant(int m, int n, int k, const int8_t* A, int lda, const 
 int g_force_bn = 0;          // test/tuning hook (b200_gemm_debug_set_bn): 0 = heuristic
 int g_group_rows = 0;         // tuning hook: rows per raster group of the tensor-core kernels (0 = 2048)
 int g_force_cg = 0;           // test/tuning hook (b200_gemm_debug_set_cta_group): 0 = auto, 1, 2
+int g_epi8 = 0;               // tuning hook (b200_gemm_debug_set_epilogue bit 1): pair kernels of the plain kinds with 8 epilogue warps
 int g_epi_direct = 0;         // tuning hook (b200_gemm_debug_set_epilogue): 1 = direct register stores for non-folding passes
 int g_ffma_fat = -1;          // strict kernel: 1 = 128x256 fat-thread variant, 0 = 128x128, -1 = by size
 int g_ffma_halves = 1;        // strict kernel: split the tail round into half tiles (tuning hook)
 
-template <int KIND, int BN, int STAGES, typename OutT, class Prod = ProdSingle, int A_ROW_BYTES = 128, int CG = 1>
+template <int KIND, int BN, int STAGES, typename OutT, class Prod = ProdSingle, int A_ROW_BYTES = 128, int CG = 1, int EPIW = 4>
 int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_total, int a_plane_rows,
               const void* B, long long ldb, int b_rows_total, int b_plane_rows, void* C, int ldc,
               cudaStream_t st, const char* name, int chunk_k = 0, const float* row_max = nullptr,
               const float* col_max = nullptr, int accumulate = 0) {
-  using Cfg = TcConfig<KIND, BN, STAGES, Prod, A_ROW_BYTES, CG>;
+  using Cfg = TcConfig<KIND, BN, STAGES, Prod, A_ROW_BYTES, CG, EPIW>;
   using T = KindTraits<KIND>;
   constexpr CUtensorMapDataType dt = KIND == KIND_F16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                    : KIND == KIND_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
@@ -285,8 +289,9 @@ int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_tota
   p.dbg_b_lbo = g_dbg_b_lbo; p.dbg_b_sbo = g_dbg_b_sbo;
   p.row_max = row_max; p.col_max = col_max;
   p.accumulate = accumulate;
+  p.axpby = t_epi.axpby; p.alpha = t_epi.alpha; p.beta = t_epi.beta;
   p.epi_direct = g_epi_direct;
-  auto kern = gemm_tc_kernel<KIND, BN, STAGES, OutT, Prod, A_ROW_BYTES, CG>;
+  auto kern = gemm_tc_kernel<KIND, BN, STAGES, OutT, Prod, A_ROW_BYTES, CG, EPIW>;
   if (int arc = ensure_smem_attr(kern, Cfg::SMEM_BYTES)) return arc;
   int tiles = p.tiles_m * p.tiles_n;
   const int units_max = t_ctx->sms / CG;                 // CTAs, or CTA pairs (one per TPC)
@@ -300,7 +305,7 @@ int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_tota
     if (split > 4) split = 4;
     if (split > num_kb / 8) split = num_kb / 8;       // keep >= 8 k-blocks per part
     if (split < 1) split = 1;
-    if (rem * CG * 4 > 1024) split = 1;               // flag slot capacity
+    if (rem * CG * Cfg::EPI_WARPS > 1024) split = 1;  // flag slot capacity
   }
   // When at least one full round exists, the partial last round is better served by half-width tiles
   // (no K split, no fold): 2*rem items of half the duration.  Needs BN/2 to be a whole number of
@@ -373,6 +378,8 @@ bool use_pair(int m, int n) {
 }
 
 #define TC_PLAIN(KIND, OUT, NAME)                                                                     \
+  if (use_pair(m, n) && g_epi8)                                                                       \
+    return launch_tc<KIND, 256, 6, OUT, ProdSingle, 128, 2, 8>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, NAME "_2cta_256x256_e8"); \
   if (use_pair(m, n))                                                                                 \
     return launch_tc<KIND, 256, 6, OUT, ProdSingle, 128, 2>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, NAME "_2cta_256x256"); \
   switch (pick_bn(m, n, true)) {                                                                      \
@@ -382,6 +389,8 @@ bool use_pair(int m, int n) {
   }
 
 int tc_tf32(int m, int n, int k, const float* A, int lda, const float* B, int ldb, float* C, int ldc, cudaStream_t st, int acc = 0) {
+  if (use_pair(m, n) && g_epi8)
+    return launch_tc<KIND_TF32, 256, 6, float, ProdSingle, 128, 2, 8>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_tf32_2cta_256x256_e8", 0, nullptr, nullptr, acc);
   if (use_pair(m, n))
     return launch_tc<KIND_TF32, 256, 6, float, ProdSingle, 128, 2>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_tf32_2cta_256x256", 0, nullptr, nullptr, acc);
   switch (pick_bn(m, n, true)) {
@@ -398,6 +407,8 @@ int tc_bf16_bf16(int m, int n, int k, const void* A, int lda, const void* B, int
 }
 int tc_s8(int m, int n, int k, const void* A, int lda, const void* B, int ldb, void* C, int ldc, cudaStream_t st) {
   // int8 column blocks are 128 elements wide (128 B): BN = 192 is not a whole number of them
+  if (use_pair(m, n) && g_epi8)
+    return launch_tc<KIND_I8, 256, 6, int32_t, ProdSingle, 128, 2, 8>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_s8_2cta_256x256_e8");
   if (use_pair(m, n))
     return launch_tc<KIND_I8, 256, 6, int32_t, ProdSingle, 128, 2>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_s8_2cta_256x256");
   if (pick_bn(m, n, true, false) == 256)
@@ -408,6 +419,8 @@ int tc_s8(int m, int n, int k, const void* A, int lda, const void* B, int ldb, v
 // int8 in, int8 out through the requantising epilogue (scales / bias ride in the row_max / col_max slots)
 int tc_s8_requant(int m, int n, int k, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
                   const float* scales, const float* bias, cudaStream_t st) {
+  if (use_pair(m, n) && g_epi8)
+    return launch_tc<KIND_I8, 256, 6, s8_out, ProdSingle, 128, 2, 8>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_s8_requant_2cta_256x256_e8", 0, scales, bias);
   if (use_pair(m, n))
     return launch_tc<KIND_I8, 256, 6, s8_out, ProdSingle, 128, 2>(m, n, k, A, lda, m, 0, B, ldb, k, 0, C, ldc, st, "tc_s8_requant_2cta_256x256", 0, scales, bias);
   if (pick_bn(m, n, true, false) == 256)
@@ -419,7 +432,7 @@ int tc_s8_requant(int m, int n, int k, const void* A, int lda, const void* B, in
 // Workspace for the bf16 planes: cached, grow-only (no per-call cudaMalloc in steady state).  Calls
 // in split modes are serialised on this buffer by stream order; use one stream per library instance.
 // K extent accumulated inside the tensor core before folding into C (0 = whole K): [0] BF16X3, [1] BF16X2
-int g_split_chunk_k[2] = {512, 1024};
+int g_split_chunk_k[2] = {512, 512};
 // Grows the device's split workspace to `need` bytes.  Starts at 256 MiB (every size of the reference's
 // 256..4096 sweep fits: its harness averages the first, cold call into each row, and a cudaFree +
 // cudaMalloc there costs tens of ms) and at least doubles.  Growth synchronises the device (other
@@ -501,7 +514,7 @@ int gemm_f32_split(int m, int n, int k, const float* A, int lda, const float* B,
     if (bn == 256)
       return launch_tc<KIND_F16, 256, 4, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x2_128x256", g_split_chunk_k[1], nullptr, nullptr, acc);
     if (bn == 192)
-      return launch_tc<KIND_F16, 192, 5, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x2_128x192", g_split_chunk_k[1], nullptr, nullptr, acc);
+      return launch_tc<KIND_F16, 192, 4, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x2_128x192", g_split_chunk_k[1], nullptr, nullptr, acc);
     return launch_tc<KIND_F16, 128, 6, float, ProdX2, 64>(m, n, k, pA, pka, NP * m, m, pB, pnb, NP * kp, kp, C, ldc, st, "tc_bf16x2_128x128", g_split_chunk_k[1], nullptr, nullptr, acc);
   }
 }
@@ -566,7 +579,7 @@ int gemm_f16x2_core(int m, int n, int k, const F16Operand& a, const F16Operand& 
                                                            b.planes, b.pitch, NP * b.plane_rows, b.plane_rows, C, ldc, st,
                                                            "tc_f16x2_128x256", g_split_chunk_k[1], a.maxv, b.maxv, acc);
   if (bn == 192)
-    return launch_tc<KIND_FP16, 192, 5, float, ProdX2, 64>(m, n, k, a.planes, a.pitch, NP * a.plane_rows, a.plane_rows,
+    return launch_tc<KIND_FP16, 192, 4, float, ProdX2, 64>(m, n, k, a.planes, a.pitch, NP * a.plane_rows, a.plane_rows,
                                                            b.planes, b.pitch, NP * b.plane_rows, b.plane_rows, C, ldc, st,
                                                            "tc_f16x2_128x192", g_split_chunk_k[1], a.maxv, b.maxv, acc);
   return launch_tc<KIND_FP16, 128, 6, float, ProdX2, 64>(m, n, k, a.planes, a.pitch, NP * a.plane_rows, a.plane_rows,
@@ -780,7 +793,7 @@ void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes) { g_dbg_b_lbo = lb
 void b200_gemm_debug_set_bn(int bn) { g_force_bn = bn; }
 void b200_gemm_debug_set_cta_group(int cg) { g_force_cg = cg; }
 void b200_gemm_debug_set_split_tail(int on) { g_split_tail = on; }
-void b200_gemm_debug_set_epilogue(int direct) { g_epi_direct = direct; }
+void b200_gemm_debug_set_epilogue(int v) { g_epi_direct = v & 1; g_epi8 = (v >> 1) & 1; }
 void b200_gemm_debug_set_group_rows(int rows) { g_group_rows = rows; }
 void b200_gemm_debug_set_ffma_variant(int v) { g_ffma_halves = v & 1; g_ffma_fat = v < 0 ? -1 : (v >> 1) & 1; }
 void b200_gemm_debug_set_split_chunk(int x3_k, int x2_k) { g_split_chunk_k[0] = x3_k; g_split_chunk_k[1] = x2_k; }
@@ -802,6 +815,44 @@ int b200_gemm_debug_kernel_time_ms(double* sum_ms) {
 int b200_gemm_f32(int m, int n, int k, const float* dA, int lda, const float* dB, int ldb, float* dC,
                   int ldc, int precision_mode, void* stream) {
   return gemm_f32_impl(m, n, k, dA, lda, dB, ldb, dC, ldc, precision_mode, 0, (cudaStream_t)stream);
+}
+
+// C = alpha * A*B + beta * C (the contract of the reference's cuBLAS comparator, cuda/MMult_cuBLAS_1.cpp:11-19).
+int b200_gemm_f32_ex(int m, int n, int k, float alpha, const float* dA, int lda, const float* dB, int ldb, float beta,
+                     float* dC, int ldc, int precision_mode, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (alpha == 1.f && beta == 0.f) return gemm_f32_impl(m, n, k, dA, lda, dB, ldb, dC, ldc, precision_mode, 0, st);
+  if (alpha == 1.f && beta == 1.f) return gemm_f32_impl(m, n, k, dA, lda, dB, ldb, dC, ldc, precision_mode, 1, st);
+  int rc = check_args(m, n, k, dA, lda, dB, ldb, dC, ldc);
+  if (rc == 1) return 0;
+  if (rc) return rc;
+  rc = ensure_device();
+  if (rc) return rc;
+  const int mode = resolve_f32_mode(precision_mode);
+  const bool cuda_core = mode == B200_F32_STRICT || !tma_ok(dA, lda, dB, ldb, 4) || k == 0 ||
+                         (precision_mode == B200_F32_AUTO && (double)m * n * k <= 2.0e8);
+  const dim3 sg((n + 255) / 256, m < 4096 ? m : 4096);
+  if (alpha == 0.f || cuda_core) {
+    // CUDA-core paths (strict FFMA chain, generic kernels): C <- (beta/alpha) C, C += A*B, C <- alpha C.
+    // beta == 0 must not read C (NaN-safe, as cuBLAS): start from C = A*B instead.
+    if (alpha == 0.f || k == 0) {
+      if (beta == 0.f) return launch_zero<float>(m, n, dC, ldc, st);
+      scale_inplace_kernel<<<sg, 256, 0, st>>>(m, n, dC, ldc, beta);
+      g_launches++;
+      return last_launch_status();
+    }
+    if (beta != 0.f && beta != alpha) { scale_inplace_kernel<<<sg, 256, 0, st>>>(m, n, dC, ldc, beta / alpha); g_launches++; }
+    rc = gemm_f32_impl(m, n, k, dA, lda, dB, ldb, dC, ldc, cuda_core && mode != B200_F32_STRICT && tma_ok(dA, lda, dB, ldb, 4) ? B200_F32_STRICT : mode,
+                       beta != 0.f ? 1 : 0, st);
+    if (rc) return rc;
+    scale_inplace_kernel<<<sg, 256, 0, st>>>(m, n, dC, ldc, alpha);
+    g_launches++;
+    return last_launch_status();
+  }
+  t_epi.axpby = 1; t_epi.alpha = alpha; t_epi.beta = beta;      // tensor-core modes: fused into the epilogue
+  rc = gemm_f32_impl(m, n, k, dA, lda, dB, ldb, dC, ldc, mode, 0, st);
+  t_epi = EpiOpts();
+  return rc;
 }
 
 int b200_gemm_f32_acc(int m, int n, int k, const float* dA, int lda, const float* dB, int ldb, float* dC,
@@ -1022,7 +1073,7 @@ int b200_gemm_f32_host(int m, int n, int k, const float* A, int lda, const float
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(t_ctx->host_mu);
   float *dA = nullptr, *dB = nullptr, *dC = nullptr;
-  const int mode = resolve_f32_mode(precision_mode);
+  const int mode = precision_mode;   // unresolved: AUTO keeps its small-problem switch to the bit-exact STRICT kernel
   // device images: pitches rounded up to 4 floats so the TMA paths apply to any k, n
   const int pk = (k + 3) & ~3, pn = (n + 3) & ~3;
   const size_t pa = (size_t)pk * 4, pb = (size_t)pn * 4, pc = (size_t)pn * 4;

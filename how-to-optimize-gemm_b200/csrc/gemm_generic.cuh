@@ -115,6 +115,12 @@ __global__ void convert_f32_to_bf16_kernel(const float* __restrict__ src, uint16
 }
 
 // C(i,j) += T(i,j): the CPU harness contract C += A*B (aarch64/MMult0.cpp:16) on top of C = A*B.
+// C *= s over an m x n window (the beta / alpha passes of the general epilogue on the CUDA-core paths)
+__global__ void scale_inplace_kernel(int M, int N, float* __restrict__ C, long long ldc, float s) {
+  for (int r = blockIdx.y; r < M; r += gridDim.y)
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) C[(long long)r * ldc + c] *= s;
+}
+
 template <typename T>
 __global__ void add_inplace_kernel(int M, int N, T* __restrict__ C, long long ldc,
                                    const T* __restrict__ Tm, long long ldt) {

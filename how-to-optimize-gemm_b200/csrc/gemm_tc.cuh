@@ -82,14 +82,25 @@ struct TcParams {
   // fp16 split; the epilogue multiplies back by 2^e(row) * 2^e(col), exact.  Null = no scaling.
   const float* row_max;    // [M] max |A(i,:)|
   const float* col_max;    // [N] max |B(:,j)|
+  // General epilogue C = alpha * (A*B) + beta * C (cuBLAS semantics, cuda/MMult_cuBLAS_1.cpp:11-19); fp32 output
+  // only.  axpby == 0: alpha = 1 and beta = accumulate (the two contracts the reference's harnesses use).
+  float alpha, beta;
+  int axpby;
   int accumulate;
   int epi_direct;     // 1: non-folding passes store straight from registers (tuning hook)          // 1: C += A*B (every partial, including the first, is folded into C); fp32/int32 only
   int dbg_b_lbo, dbg_b_sbo;  // 0 = defaults (probe hook, see b200_gemm_debug_set_b_desc)
 };
 
-template <int KIND, int BN, int STAGES, class Prod, int A_ROW_BYTES, int CG = 1>
+// REGACC (split-precision fp32 modes): the running fp32 sum of a tile lives in the REGISTERS of eight
+// epilogue warps (lane = row, 128 columns per warp) and every K-chunk's TMEM accumulator is added to it
+// with a rounded fp32 add; C is touched once per tile.  Otherwise four epilogue warps drain one
+// accumulator per tile.
+template <int KIND, int BN, int STAGES, class Prod, int A_ROW_BYTES, int CG = 1, int EPIW = 4>
 struct TcConfig {
   using T = KindTraits<KIND>;
+  static constexpr bool REGACC = Prod::N > 1;
+  static constexpr int EPI_WARPS = REGACC ? 8 : EPIW;          // EPIW = 8: two warps per TMEM lane quadrant, half the column passes each
+  static constexpr int EPI_WARP0 = REGACC ? 4 : 2;             // first epilogue warp (warpgroup-aligned for setmaxnreg)
   static constexpr int BM = 128;
   static constexpr int BK = A_ROW_BYTES / T::ELEM;          // one swizzled row of K per stage
   static constexpr int A_PLANE = BM * A_ROW_BYTES;          // 16 KB (SW128) or 8 KB (SW64)
@@ -107,13 +118,14 @@ struct TcConfig {
   static constexpr int MMAS_PER_STAGE = BK / T::UMMA_K;
   static constexpr int A_KADV = T::UMMA_K * T::ELEM;        // 32 B inside the swizzled row
   static constexpr int B_KADV = T::UMMA_K * 128;            // UMMA_K k-rows of 128 B
-  static constexpr int EPI_STAGING = 4 * 32 * 128;          // 4 warps x 32 rows x 128 B
+  static constexpr int EPI_STAGING = EPI_WARPS * 32 * 128;  // per epilogue warp: 32 rows x 128 B
   static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;  // TMEM columns between the two accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_STAGING +
                                     NUM_BARS * 8 + 16;
-  static constexpr int THREADS = 192;
+  static constexpr int THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
+  static_assert(!REGACC || BN % 64 == 0, "register accumulation splits the tile columns over two warp sets of 32-column groups");
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
   static_assert(BN_CTA % B_BOX_COLS == 0 && BN % 16 == 0 && BN <= 256, "invalid BN");
   static constexpr int TILE_M = 128 * CG;                   // rows of C per work unit (CTA or CTA pair)
@@ -210,11 +222,11 @@ template <typename OutT> struct OutBytes { static constexpr int V = 4; };
 template <> struct OutBytes<bf16_out> { static constexpr int V = 2; };
 template <> struct OutBytes<s8_out> { static constexpr int V = 1; };
 
-template <int KIND, int BN, int STAGES, typename OutT, class Prod, int A_ROW_BYTES, int CG>
-__global__ void __launch_bounds__(192, 1)
+template <int KIND, int BN, int STAGES, typename OutT, class Prod, int A_ROW_BYTES, int CG, int EPIW>
+__global__ void __launch_bounds__((TcConfig<KIND, BN, STAGES, Prod, A_ROW_BYTES, CG, EPIW>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
-  using Cfg = TcConfig<KIND, BN, STAGES, Prod, A_ROW_BYTES, CG>;
+  using Cfg = TcConfig<KIND, BN, STAGES, Prod, A_ROW_BYTES, CG, EPIW>;
   using T = KindTraits<KIND>;
   constexpr int OB = OutBytes<OutT>::V;
 
@@ -249,7 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 4 * CG);     // one arrive per epilogue warp of every CTA in the pair
+      mbar_init(bar_tempty + 8 * i, Cfg::EPI_WARPS * CG);     // one arrive per epilogue warp of every CTA in the pair
     }
     fence_barrier_init();
   }
@@ -266,6 +278,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_items = p.full_tiles + (num_tiles - p.full_tiles) * (p.halfn ? 2 : p.split);
   const int num_kb = (p.K + Cfg::BK - 1) / Cfg::BK;
 
+  if (warp < Cfg::EPI_WARP0) {
+  // register pool of the CTA = 384 threads x 168 (launch bound); afterwards 128 x 88 + 256 x 208 = the same 64512
+  if constexpr (Cfg::REGACC) setmaxnreg_dec<88>();   // data-movement warpgroup (incl. its two idle warps) gives registers back
   if (warp == 0) {
     // ===================== TMA producer =====================
     // The whole warp walks the loop (warp-uniform control flow keeps stage/phase/coordinates in uniform
@@ -363,10 +378,148 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
        }
       }
     }
+  }
   } else {
-    // ===================== epilogue (4 warps) =====================
+   if constexpr (Cfg::REGACC) {
+    setmaxnreg_inc<208>();
+    // ===================== epilogue, register-resident two-level accumulation (8 warps) =====================
+    // The tensor core adds into its fp32 accumulator with truncation, so a long K chain drifts (measured:
+    // error grows ~K).  K is cut into chunks; each chunk gets a fresh TMEM accumulator and is added HERE,
+    // with a rounded fp32 add, to the tile's running sum, which lives in registers: lane = row (TMEM lane
+    // quadrant warp % 4), warps 4-7 own tile columns [0, bn/2), warps 8-11 own [bn/2, bn).  C is written
+    // once per tile (read once more only for C += A*B and for the K-split tail parts).
+    const int ew = warp - Cfg::EPI_WARP0;
+    const int q = ew & 3;
+    const int half = ew >> 2;
+    uint8_t* stg = smem_gen + (sEpi - smem_base) + ew * 4096;   // 32 rows x 128 B, chunk-swizzled
+    constexpr int HC = BN / 2;                       // columns per warp in a full-width tile
+    constexpr int NJ = HC / 32;                      // 32-column register groups
+    int as = 0;
+    uint32_t aph = 0;
+    const uint32_t tempty_base = CG == 2 ? mapa(bar_tempty, 0) : bar_tempty;   // leader's barrier
+    for (int w = unit; w < num_items; w += num_units) {
+      const WorkItem it = work_item<BN>(w, p, num_kb);
+      int mb, nb;
+      tile_coords(it.tile, p.tiles_m, p.tiles_n, p.group_m, mb, nb);
+      const int hc = it.bn / 2;                      // columns this warp owns (HC, or HC/2 in a half-width tile)
+      const int nj = hc / 32;
+      const int m0 = mb * Cfg::TILE_M + (int)cta_rank * Cfg::BM + q * 32;
+      const int n0 = nb * BN + it.nsub * it.bn + half * hc;
+      const uint32_t t_col = (uint32_t)(half * hc);
+      float acc[NJ][32];
+      bool first = true;
+      for (int c0 = it.kb0; c0 < it.kb1; c0 += p.chunk_kb) {
+        mbar_wait(bar_tfull + 8 * as, aph);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::ACC_STRIDE + t_col;
+#pragma unroll
+        for (int j = 0; j < NJ; j++) {
+          if (j < nj) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_addr + j * 32, r);
+            tmem_ld_wait();
+            if (first) {
+#pragma unroll
+              for (int i = 0; i < 32; i++) acc[j][i] = __uint_as_float(r[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i++) acc[j][i] = __fadd_rn(acc[j][i], __uint_as_float(r[i]));
+            }
+          }
+        }
+        first = false;
+        tc_fence_before();                            // accumulator drained: hand the TMEM stage back
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(tempty_base + 8 * as);
+          else mbar_arrive(bar_tempty + 8 * as);
+        }
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+      // ---- the tile's single pass over C ----
+      int* flag = p.flags + ((it.tile - p.full_tiles) * CG + (int)cta_rank) * Cfg::EPI_WARPS + ew;
+      if (it.part > 0) {                               // K-split tail: wait until parts < it.part are in C
+        if (lane == 0) {
+          const long long t0 = clock64();
+          while (true) {
+            int v;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v == it.part) break;
+            if (clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }
+          }
+        }
+        __syncwarp();
+      }
+      // beta * C is read by part 0 only; later K parts add alpha * partial to what is already there
+      const bool fold = p.accumulate != 0 || it.part > 0 || (p.axpby && p.beta != 0.f);
+      const float al = p.axpby ? p.alpha : 1.f;
+      const float be = (p.axpby && it.part == 0) ? p.beta : 1.f;
+      const int chunk = lane & 7;
+#pragma unroll
+      for (int j = 0; j < NJ; j++) {
+        if (j < nj) {
+          const int col = n0 + j * 32 + chunk * 4;
+          const bool vec = p.vec_ok && col + 4 <= p.N;
+          // registers (row = lane) -> staging, 16-byte chunk index XOR (row & 7): conflict-free both ways
+#pragma unroll
+          for (int g = 0; g < 8; g++) {
+            uint4 v = make_uint4(__float_as_uint(acc[j][4 * g]), __float_as_uint(acc[j][4 * g + 1]),
+                                 __float_as_uint(acc[j][4 * g + 2]), __float_as_uint(acc[j][4 * g + 3]));
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((g ^ (lane & 7)) << 4)) = v;
+          }
+          __syncwarp();
+          int ce[4] = {0, 0, 0, 0};
+          if (p.col_max != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+              if (col + e < p.N) ce[e] = pow2_exp(__ldg(p.col_max + col + e));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int row = i * 4 + (lane >> 3);
+            const int gm = m0 + row;
+            float4 v = *reinterpret_cast<const float4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4));
+            if (gm < p.M) {
+              if (p.row_max != nullptr) {                // undo the operand scaling: exact powers of two
+                const int re = pow2_exp(__ldg(p.row_max + gm));
+                v.x = mul_pow2(v.x, re + ce[0]); v.y = mul_pow2(v.y, re + ce[1]);
+                v.z = mul_pow2(v.z, re + ce[2]); v.w = mul_pow2(v.w, re + ce[3]);
+              }
+              float* dst = reinterpret_cast<float*>(p.C) + (long long)gm * p.ldc + col;
+              if (p.axpby) { v.x *= al; v.y *= al; v.z *= al; v.w *= al; }
+              if (vec) {
+                if (fold) {                              // once per tile: C += A*B, beta * C, or an earlier K part
+                  const float4 o = __ldcg(reinterpret_cast<const float4*>(dst));
+                  if (p.axpby) { v.x = fmaf(be, o.x, v.x); v.y = fmaf(be, o.y, v.y); v.z = fmaf(be, o.z, v.z); v.w = fmaf(be, o.w, v.w); }
+                  else { v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                }
+                *reinterpret_cast<float4*>(dst) = v;
+              } else {
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                  if (col + e < p.N) dst[e] = !fold ? vv[e] : p.axpby ? fmaf(be, __ldcg(dst + e), vv[e]) : vv[e] + __ldcg(dst + e);
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      if (w >= p.full_tiles && p.split > 1) {          // publish this part (the last one re-arms the flag)
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          const int nv = it.part + 1 == p.split ? 0 : it.part + 1;
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(nv) : "memory");
+        }
+      }
+    }
+   } else {
+    // ===================== epilogue (4 or 8 warps) =====================
     const int q = warp & 3;                          // TMEM lane quadrant this warp may read
-    uint8_t* stg = smem_gen + (sEpi - smem_base) + q * 4096;   // 32 rows x 128 B, chunk-swizzled
+    const int ew = warp - Cfg::EPI_WARP0;
+    const int ehalf = ew >> 2;                       // 8 warps: which half of the column passes this warp drains
+    uint8_t* stg = smem_gen + (sEpi - smem_base) + ew * 4096;   // 32 rows x 128 B, chunk-swizzled
     constexpr int COLS = OutPack<OutT>::COLS;
     constexpr int VEC_ELEMS = 16 / OB;
     int as = 0;
@@ -388,7 +541,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (hb) bi = __ldg(p.col_max + m0 + lane);
         }
       }
-      int* flag = p.flags + ((it.tile - p.full_tiles) * CG + (int)cta_rank) * 4 + q;
+      int* flag = p.flags + ((it.tile - p.full_tiles) * CG + (int)cta_rank) * Cfg::EPI_WARPS + ew;
       if (it.part > 0) {                               // wait until parts < it.part are in C
         if (lane == 0) {
           const long long t0 = clock64();
@@ -405,19 +558,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
      // accumulator with truncation, so a long K chain drifts (measured: error grows ~K).  Each
      // K-chunk gets a fresh TMEM accumulator and is folded into C here with a rounded fp32 add.
      for (int c0 = it.kb0; c0 < it.kb1; c0 += p.chunk_kb) {
-      const bool fold = p.accumulate != 0 || c0 != it.kb0 || it.part > 0;
+      const bool fold = p.accumulate != 0 || c0 != it.kb0 || it.part > 0 || (p.axpby && p.beta != 0.f);
+      const float al = p.axpby ? p.alpha : 1.f;
+      const float be = (p.axpby && it.part == 0 && c0 == it.kb0) ? p.beta : 1.f;
       mbar_wait(bar_tfull + 8 * as, aph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::ACC_STRIDE;
 #pragma unroll 1
-      for (int ps = 0; ps < passes; ps++) {
+      const int ps0 = Cfg::EPI_WARPS == 8 ? ehalf * (passes >> 1) : 0;
+      const int ps1 = Cfg::EPI_WARPS == 8 ? (ehalf == 0 ? (passes >> 1) : passes) : passes;
+      if (ps0 == ps1) {                              // (8 warps, a single-pass tile) nothing to drain here: still release the stage
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(tempty_base + 8 * as);
+          else mbar_arrive(bar_tempty + 8 * as);
+        }
+      }
+      for (int ps = ps0; ps < ps1; ps++) {
        if constexpr (std::is_same<OutT, s8_out>::value) {
         // Requantising epilogue: lane = row, 32 accumulator columns -> 32 bytes, stored straight from
         // registers as two 16-byte vectors (whole 32-byte sectors; no staging transpose needed).
         uint32_t ra[32];
         tmem_ld_32x32b_x32(t_addr + ps * 32, ra);
         tmem_ld_wait();
-        if (ps == passes - 1) {
+        if (ps == ps1 - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -468,7 +633,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_32x32b_x32(t_addr + ps * (COLS == 64 ? 64 : 32), ra);
         if constexpr (COLS == 64) tmem_ld_32x32b_x32(t_addr + ps * 64 + 32, rb);
         tmem_ld_wait();
-        if (ps == passes - 1) {                      // TMEM stage fully drained: hand it back early
+        if (ps == ps1 - 1) {                         // this warp's share of the TMEM stage is drained: hand it back early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -477,7 +642,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         OutPack<OutT>::pack(ra, rb, w);
-        if (p.epi_direct && !fold && p.row_max == nullptr && p.vec_ok && n0 + (ps + 1) * COLS <= p.N) {
+        if (p.epi_direct && !fold && !p.axpby && p.row_max == nullptr && p.vec_ok && n0 + (ps + 1) * COLS <= p.N) {
           // Direct epilogue: lane = row holds 128 contiguous bytes of C for this pass; eight 16-byte stores
           // straight from registers (32 rows per instruction, whole lines after the eighth) — no staging
           // round trip, no warp syncs.
@@ -524,7 +689,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint8_t* dst = reinterpret_cast<uint8_t*>(p.C) + ((long long)gm * p.ldc + col) * OB;
             if (vec) {
               if constexpr (std::is_same<OutT, float>::value) {
-                if (fold) {
+                if (p.axpby) {
+                  const float4 o = fold ? old[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                  v.x = __float_as_uint(fmaf(be, o.x, al * __uint_as_float(v.x)));
+                  v.y = __float_as_uint(fmaf(be, o.y, al * __uint_as_float(v.y)));
+                  v.z = __float_as_uint(fmaf(be, o.z, al * __uint_as_float(v.z)));
+                  v.w = __float_as_uint(fmaf(be, o.w, al * __uint_as_float(v.w)));
+                } else if (fold) {
                   v.x = __float_as_uint(__uint_as_float(v.x) + old[i].x);
                   v.y = __float_as_uint(__uint_as_float(v.y) + old[i].y);
                   v.z = __float_as_uint(__uint_as_float(v.z) + old[i].z);
@@ -544,7 +715,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int e = 0; e < 4; e++)
                   if (col + e < p.N) {
                     if constexpr (std::is_same<OutT, float>::value) {
-                      if (fold) vv[e] = __float_as_uint(__uint_as_float(vv[e]) + __ldcg(reinterpret_cast<const float*>(dst) + e));
+                      if (p.axpby) vv[e] = __float_as_uint(fmaf(be, fold ? __ldcg(reinterpret_cast<const float*>(dst) + e) : 0.f, al * __uint_as_float(vv[e])));
+                      else if (fold) vv[e] = __float_as_uint(__uint_as_float(vv[e]) + __ldcg(reinterpret_cast<const float*>(dst) + e));
                     } else if constexpr (std::is_same<OutT, int32_t>::value) {
                       if (fold) vv[e] += __ldcg(reinterpret_cast<const uint32_t*>(dst) + e);
                     }
@@ -573,6 +745,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+  }
+
   }
 
   tc_fence_before();

@@ -250,6 +250,11 @@ __device__ __forceinline__ int32_t requant_s8(int32_t acc, float scale, float bi
   return f != f ? 0 : q;
 }
 
+// Register re-balancing between warpgroups (4 aligned warps): data-movement warps give registers back,
+// the epilogue warps that keep a tile's running sum in registers take them.
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));

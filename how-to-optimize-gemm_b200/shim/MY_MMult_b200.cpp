@@ -36,14 +36,15 @@ void MY_MMult(cublasHandle_t, int m, int n, int k, float* d_A, int lda, float* d
 }
 
 // aarch64/ harness: host pointers, C pre-zeroed by the caller, C += A*B
-// (aarch64/test_MMult.cpp:107-110).  Device pointers are accepted too (C = A*B, like above).
+// (aarch64/test_MMult.cpp:107-110).  Device pointers are accepted too, with the SAME contract: the 9-argument
+// form always means C += A*B (aarch64/MMult0.cpp:16), wherever the operands live.
 void MY_MMult(int m, int n, int k, float* a, int lda, float* b, int ldb, float* c, int ldc) {
   cudaPointerAttributes at;
   const bool on_device =
       cudaPointerGetAttributes(&at, c) == cudaSuccess && at.type == cudaMemoryTypeDevice;
   cudaGetLastError();
   if (on_device)
-    die_on(b200_gemm_f32(m, n, k, a, lda, b, ldb, c, ldc, B200_F32_AUTO, nullptr), "MY_MMult(device)");
+    die_on(b200_gemm_f32_acc(m, n, k, a, lda, b, ldb, c, ldc, B200_F32_AUTO, nullptr), "MY_MMult(device)");
   else
     die_on(b200_gemm_f32_host(m, n, k, a, lda, b, ldb, c, ldc, B200_F32_AUTO), "MY_MMult(host)");
 }

@@ -109,6 +109,15 @@ int b200_gemm_f32_acc(int m, int n, int k,
                       const float* dA, int lda, const float* dB, int ldb,
                       float* dC, int ldc, int precision_mode, void* stream);
 
+/* fp32: C = alpha * A*B + beta * C on DEVICE pointers — the contract of the reference's cuBLAS comparator
+ * (cublasSgemm, cuda/MMult_cuBLAS_1.cpp:11-19; the harness only ever passes alpha = 1, beta = 0).  beta == 0
+ * never reads C.  (1, 0) and (1, 1) are b200_gemm_f32 / b200_gemm_f32_acc exactly; any other pair is fused
+ * into the epilogue of the tensor-core modes, and costs two element-wise passes over C around the kernel in
+ * STRICT mode and on the generic (unaligned-operand) path. */
+int b200_gemm_f32_ex(int m, int n, int k, float alpha,
+                     const float* dA, int lda, const float* dB, int ldb, float beta,
+                     float* dC, int ldc, int precision_mode, void* stream);
+
 /* fp32 with HOST pointers and the CPU harness contract C += A*B
  * (aarch64/MMult0.cpp:11-19; harness zeroes C first, aarch64/test_MMult.cpp:107).
  * Stages H2D, runs b200_gemm_f32 on the device, adds into C on the device,

@@ -249,12 +249,12 @@ def test_full_size_s8_requant_4096(gemm, oracle):
     assert torch.equal(out, t)
 
 
-@pytest.mark.parametrize("mode", ["x3", "x2"])
+@pytest.mark.parametrize("mode", ["x3", "x2", "f16x2"])
 @pytest.mark.parametrize("m,n,k", [(300, 520, 200), (77, 96, 80), (1000, 1104, 2048), (2304, 2304, 1024)])
 def test_f32_packed_b_bit_identical(gemm, oracle, m, n, k, mode):
     """b200_gemm_f32_pack_b + b200_gemm_f32_packed == b200_gemm_f32 / _acc in the same mode, bit for bit
     (same planes, same kernel), for several A against one handle (the reuse the packing interface is for)."""
-    md = {"x3": gemm.F32_BF16X3, "x2": gemm.F32_BF16X2}[mode]
+    md = {"x3": gemm.F32_BF16X3, "x2": gemm.F32_BF16X2, "f16x2": gemm.F32_F16X2}[mode]
     b = _libs.gen_f32(oracle, k, n, 52)
     B = cuda(b)
     pk = gemm.PackedB(B, md)
@@ -271,19 +271,36 @@ def test_f32_packed_b_bit_identical(gemm, oracle, m, n, k, mode):
     gemm.gemm_f32_packed(A, pk, out=C2, accumulate=True)
     assert torch.equal(C1, C2)
     t = _libs.ref_f64(oracle, A.cpu().numpy(), b)
-    assert rel(out.cpu().numpy(), t) <= (TOL_X3 if mode == "x3" else TOL_X2)
+    assert rel(out.cpu().numpy(), t) <= {"x3": TOL_X3, "x2": TOL_X2, "f16x2": TOL_F16X2}[mode]
+    if mode == "f16x2":
+        # both operands pre-split, and a K-sliced consumer (what the row-panel plan does with B's slices):
+        # A packed once, each row block of B packed as it "arrives", products accumulated into C
+        pa = gemm.PackedA(A, md)
+        assert torch.equal(gemm.gemm_f32_packed_ab(pa, pk, torch.empty_like(out)), out)
+        if k >= 128:
+            k0 = (k // 3) // 8 * 8
+            Cs = torch.empty_like(out)
+            for j, (a0, a1) in enumerate(((0, k0), (k0, k))):
+                pbj = gemm.PackedB(B[a0:a1], md)
+                gemm.gemm_f32_packed_ab(pa, pbj, Cs, a_k0=a0, accumulate=j > 0)
+                pbj.close()
+            assert rel(Cs.cpu().numpy(), t) <= TOL_F16X2
+        pa.close()
     pk.close()
 
 
 def test_f32_packed_b_errors(gemm):
     B = torch.rand(64, 48, device="cuda")
     A = torch.rand(32, 64, device="cuda")
-    for md in (gemm.F32_STRICT, gemm.F32_TF32, gemm.F32_F16X2):
+    for md in (gemm.F32_STRICT, gemm.F32_TF32):
         with pytest.raises(gemm.B200GemmError) as e:
             gemm.PackedB(B, md)
         assert e.value.code == -3                                   # no split in these modes
-    pk = gemm.PackedB(B)                                            # AUTO = library default (BF16X3)
-    assert torch.equal(gemm.gemm_f32_packed(A, pk), gemm.gemm_f32(A, B, mode=gemm.F32_BF16X3))
+    with pytest.raises(gemm.B200GemmError) as e:
+        gemm.PackedA(A, gemm.F32_BF16X3)                            # A handles exist for F16X2 only
+    assert e.value.code == -3
+    pk = gemm.PackedB(B)                                            # AUTO = library default (F16X2)
+    assert torch.equal(gemm.gemm_f32_packed(A, pk), gemm.gemm_f32(A, B, mode=gemm.F32_F16X2))
     with pytest.raises(gemm.B200GemmError) as e:
         gemm.gemm_f32_packed(torch.rand(32, 80, device="cuda"), pk)  # k does not match the handle
     assert e.value.code == -1
@@ -448,3 +465,25 @@ def test_full_size_s8_4096(gemm, oracle):
     oracle.oracle_random_int8_ramp(N, N, _libs.P(ar), N)
     Cr = gemm.gemm_s8s32(cuda(ar), cuda(ar))
     assert np.array_equal(Cr[:64].cpu().numpy(), _libs.ref_s8(oracle, ar[:64], ar))
+
+
+@pytest.mark.parametrize("mode,tol", [("strict", 2e-6), ("tf32", TOL_TF32), ("x3", TOL_X3), ("f16x2", TOL_F16X2)])
+@pytest.mark.parametrize("alpha,beta", [(1.0, 0.0), (1.0, 1.0), (2.5, 0.0), (-0.75, 0.5), (0.0, 2.0), (3.0, 3.0)])
+@pytest.mark.parametrize("m,n,k", [(200, 136, 264), (1000, 1104, 2048), (77, 77, 77)])
+def test_f32_alpha_beta(gemm, oracle, m, n, k, alpha, beta, mode, tol):
+    """C = alpha*A*B + beta*C, the contract of the reference's cuBLAS comparator (cuda/MMult_cuBLAS_1.cpp:11-19:
+    cublasSgemm with alpha = 1, beta = 0).  beta == 0 must not read C (NaN in C stays out of the result)."""
+    md = {"strict": gemm.F32_STRICT, "tf32": gemm.F32_TF32, "x3": gemm.F32_BF16X3, "f16x2": gemm.F32_F16X2}[mode]
+    a, b, c0 = _libs.gen_f32(oracle, m, k, 61), _libs.gen_f32(oracle, k, n, 62), _libs.gen_f32(oracle, m, n, 63)
+    C = cuda(c0)
+    if beta == 0.0:
+        C[::7, ::5] = float("nan")
+    gemm.gemm_f32_ex(alpha, cuda(a), cuda(b), beta, C, mode=md)
+    ab = _libs.ref_f64(oracle, a, b)
+    want = alpha * ab + beta * c0.astype(np.float64)
+    got = C.cpu().numpy()
+    assert np.isfinite(got).all()
+    scale = abs(alpha) * np.abs(ab).max() + abs(beta) * np.abs(c0).max()
+    assert np.abs(got - want).max() <= tol * scale + 1e-30, (gemm.last_kernel(), np.abs(got - want).max() / scale)
+    if (alpha, beta) == (1.0, 0.0):
+        assert torch.equal(C, gemm.gemm_f32(cuda(a), cuda(b), mode=md))

@@ -1,0 +1,69 @@
+"""Round-2 probe: 4 vs 8 epilogue warps for the single-product pair kernels (bf16, tf32, int8, int8 requant)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import _libs
+
+g = _libs.load_pkg()
+o = _libs.load_oracle()
+dev = "cuda"
+
+
+def timeit(fn, iters=20):
+    for i in range(3):
+        fn(i)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(iters):
+        fn(i)
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+res = []
+for n in (4096, 8192, 2304):
+    R = 3 if n <= 4096 else 2
+    bf = [((torch.rand(n, n, device=dev) - 0.5).bfloat16(), (torch.rand(n, n, device=dev) - 0.5).bfloat16()) for _ in range(R)]
+    i8 = [(torch.randint(-127, 128, (n, n), device=dev, dtype=torch.int8), torch.randint(-127, 128, (n, n), device=dev, dtype=torch.int8)) for _ in range(R)]
+    f32 = [(torch.rand(n, n, device=dev) - 0.5, torch.rand(n, n, device=dev) - 0.5) for _ in range(R)]
+    sc, bi = torch.rand(n, device=dev) * 1e-4, torch.rand(n, device=dev)
+    ob = [torch.empty(n, n, device=dev, dtype=torch.bfloat16) for _ in range(R)]
+    of = [torch.empty(n, n, device=dev) for _ in range(R)]
+    oi = [torch.empty(n, n, device=dev, dtype=torch.int32) for _ in range(R)]
+    o8 = [torch.empty(n, n, device=dev, dtype=torch.int8) for _ in range(R)]
+    cases = {
+        "bf16->bf16": lambda i: g.gemm_bf16(bf[i % R][0], bf[i % R][1], out=ob[i % R]),
+        "bf16->f32": lambda i: g.gemm_bf16(bf[i % R][0], bf[i % R][1], out=of[i % R]),
+        "tf32": lambda i: g.gemm_f32(f32[i % R][0], f32[i % R][1], out=of[i % R], mode=1),
+        "s8->s32": lambda i: g.gemm_s8s32(i8[i % R][0], i8[i % R][1], out=oi[i % R]),
+        "s8 requant": lambda i: g.gemm_s8s8_requant(i8[i % R][0], i8[i % R][1], sc, bi, out=o8[i % R]),
+    }
+    ref = {}
+    for hook in (0, 2):
+        g.lib.b200_gemm_debug_set_epilogue(hook)
+        for name, fn in cases.items():
+            ms = timeit(fn)
+            fn(0)
+            torch.cuda.synchronize()
+            outt = {"bf16->bf16": ob, "bf16->f32": of, "tf32": of, "s8->s32": oi, "s8 requant": o8}[name][0]
+            key = (name, n)
+            same = None
+            if hook == 0:
+                ref[key] = outt.clone()
+            else:
+                same = bool(torch.equal(ref[key], outt))
+            res.append({"n": n, "case": name, "epi_warps": 8 if hook else 4, "ms": ms, "tops": 2.0 * n ** 3 / ms / 1e9,
+                        "kernel": g.last_kernel(), "identical_to_4_warp": same})
+            print(res[-1], flush=True)
+    g.lib.b200_gemm_debug_set_epilogue(0)
+    del bf, i8, f32, ob, of, oi, o8, ref
+    torch.cuda.empty_cache()
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "probe_epi8.json"), "w"), indent=1)

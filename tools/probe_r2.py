@@ -68,16 +68,16 @@ print(out["f16x2_pieces"], flush=True)
 
 # raster group x chunk sweep on the GEMM alone
 sweep = []
-for grp in (1024, 2048, 4096):
+for grp in (2048, 4096):
     g.lib.b200_gemm_debug_set_group_rows(grp)
-    for ck in (512, 1024, 2048, 4096):
+    for ck in (256, 512, 1024, 4096):
         g.lib.b200_gemm_debug_set_split_chunk(512, ck)
         ms = timeit(lambda i: g.gemm_f32_packed_ab(pas[i % R], pbs[i % R], sets[i % R][2]), iters=10)
         g.gemm_f32_packed_ab(pas[0], pbs[0], Cm)
         sweep.append({"group_rows": grp, "chunk_k": ck, "ms": ms, "tflops": flops / ms / 1e9, "rel_err": err(Cm)})
         print(sweep[-1], flush=True)
 g.lib.b200_gemm_debug_set_group_rows(0)
-g.lib.b200_gemm_debug_set_split_chunk(512, 1024)
+g.lib.b200_gemm_debug_set_split_chunk(512, 512)
 out["f16x2_sweep"] = sweep
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"probe_r2_{N}.json"), "w"), indent=1)

@@ -1,5 +1,5 @@
 """Launch one kernel family a few times (for ncu captures):  python tools/run_one.py KIND N [REPS]
-KIND in {strict, tf32, bf16, bf16_obf16, s8, bf16x3, bf16x2}."""
+KIND in {strict, tf32, bf16, bf16_obf16, s8, s8_requant, bf16x3, bf16x2, f16x2}."""
 import os
 import sys
 
@@ -16,6 +16,12 @@ if kind == "s8":
     A = torch.randint(-127, 128, (n, n), device=dev, dtype=torch.int8)
     B = torch.randint(-127, 128, (n, n), device=dev, dtype=torch.int8)
     fn = lambda: g.gemm_s8s32(A, B)
+elif kind == "s8_requant":
+    A = torch.randint(-127, 128, (n, n), device=dev, dtype=torch.int8)
+    B = torch.randint(-127, 128, (n, n), device=dev, dtype=torch.int8)
+    sc = torch.rand(n, device=dev) * 1e-4
+    bi = torch.rand(n, device=dev)
+    fn = lambda: g.gemm_s8s8_requant(A, B, sc, bi)
 elif kind.startswith("bf16") and kind not in ("bf16x3", "bf16x2"):
     A = (torch.rand(n, n, device=dev) - 0.5).bfloat16()
     B = (torch.rand(n, n, device=dev) - 0.5).bfloat16()
@@ -24,7 +30,7 @@ elif kind.startswith("bf16") and kind not in ("bf16x3", "bf16x2"):
 else:
     A = torch.rand(n, n, device=dev) - 0.5
     B = torch.rand(n, n, device=dev) - 0.5
-    mode = {"strict": 0, "tf32": 1, "bf16x3": 2, "bf16x2": 3}[kind]
+    mode = {"strict": 0, "tf32": 1, "bf16x3": 2, "bf16x2": 3, "f16x2": 5}[kind]
     fn = lambda: g.gemm_f32(A, B, mode=mode)
 for _ in range(reps):
     fn()
