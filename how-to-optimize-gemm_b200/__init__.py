@@ -22,7 +22,8 @@ OUT_F32, OUT_BF16 = 0, 1
 EXPORTS = [
     "b200_gemm_version", "b200_gemm_device_ok", "b200_gemm_strerror", "b200_gemm_last_kernel",
     "b200_gemm_launch_count", "b200_gemm_default_f32_mode", "b200_gemm_set_default_f32_mode",
-    "b200_gemm_f32", "b200_gemm_f32_acc", "b200_gemm_f32_ex", "b200_gemm_f32_host", "b200_gemm_bf16", "b200_gemm_s8s32",
+    "b200_gemm_f32", "b200_gemm_f32_acc", "b200_gemm_f32_ex", "b200_gemm_workspace_bytes", "b200_gemm_reserve_workspace", "b200_mxf4_q_bytes", "b200_mxf4_sf_bytes",
+    "b200_mxf4_quantize_a", "b200_mxf4_quantize_b", "b200_gemm_mxf4", "b200_gemm_f32_host", "b200_gemm_bf16", "b200_gemm_s8s32",
     "b200_gemm_s8s32_host", "b200_gemm_s8s8_requant", "b200_gemm_f32_pack_b", "b200_gemm_f32_packed",
     "b200_gemm_f32_pack_free", "b200_nccl_load", "b200_nccl_last_error", "b200_comm_unique_id", "b200_comm_init_rank",
     "b200_comm_destroy", "b200_rowpanel_create", "b200_rowpanel_destroy", "b200_rowpanel_slices", "b200_gemm_f32_rowpanel",
@@ -55,6 +56,16 @@ lib.b200_gemm_launch_count.restype = C.c_ulonglong
 lib.b200_gemm_f32.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp]
 lib.b200_gemm_f32_acc.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp]
 lib.b200_gemm_f32_ex.argtypes = [_i, _i, _i, C.c_float, _vp, _i, _vp, _i, C.c_float, _vp, _i, _i, _vp]
+lib.b200_gemm_workspace_bytes.argtypes = [_i, _i, _i, _i]
+lib.b200_gemm_workspace_bytes.restype = C.c_size_t
+lib.b200_gemm_reserve_workspace.argtypes = [C.c_size_t]
+lib.b200_mxf4_q_bytes.argtypes = [_i, _i]
+lib.b200_mxf4_q_bytes.restype = C.c_size_t
+lib.b200_mxf4_sf_bytes.argtypes = [_i, _i]
+lib.b200_mxf4_sf_bytes.restype = C.c_size_t
+lib.b200_mxf4_quantize_a.argtypes = [_i, _i, _vp, _i, _vp, _vp, _vp]
+lib.b200_mxf4_quantize_b.argtypes = [_i, _i, _vp, _i, _vp, _vp, _vp]
+lib.b200_gemm_mxf4.argtypes = [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]
 lib.b200_gemm_f32_host.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i]
 lib.b200_gemm_bf16.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp]
 lib.b200_gemm_s8s32.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]
@@ -168,6 +179,30 @@ def gemm_f32_ex(alpha, A, B, beta, out, mode=F32_AUTO, stream=None):
     n = B.shape[1]
     _check(lib.b200_gemm_f32_ex(m, n, k, alpha, A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), beta, out.data_ptr(), _ld(out),
                                 mode, _stream_ptr(stream)))
+    return out
+
+
+def mxf4_quantize(X, transpose=False, stream=None):
+    """fp32 CUDA matrix -> (q, sf, rows, k): packed E2M1 rows + UE8M0 scale atoms (b200_mxf4_quantize_a / _b).
+    transpose=False: X is A (m x k), rows = m.  transpose=True: X is B (k x n) and the result is B^T (rows = n)."""
+    import torch
+    assert X.dtype == torch.float32 and X.is_cuda and X.dim() == 2
+    r, c = X.shape
+    rows, k = (c, r) if transpose else (r, c)
+    q = torch.empty(lib.b200_mxf4_q_bytes(rows, k), dtype=torch.uint8, device=X.device)
+    sf = torch.empty(lib.b200_mxf4_sf_bytes(rows, k), dtype=torch.uint8, device=X.device)
+    fn = lib.b200_mxf4_quantize_b if transpose else lib.b200_mxf4_quantize_a
+    _check(fn(r, c, X.data_ptr(), _ld(X), q.data_ptr(), sf.data_ptr(), _stream_ptr(stream)))
+    return q, sf, rows, k
+
+
+def gemm_mxf4(qa, sfa, qb, sfb, m, n, k, out=None, stream=None):
+    """C (m x n fp32) = dequant(A_q) * dequant(B_q)^T from mxf4_quantize outputs (b200_gemm_mxf4)."""
+    import torch
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=qa.device)
+    _check(lib.b200_gemm_mxf4(m, n, k, qa.data_ptr(), sfa.data_ptr(), qb.data_ptr(), sfb.data_ptr(), out.data_ptr(), _ld(out),
+                              _stream_ptr(stream)))
     return out
 
 

@@ -18,6 +18,7 @@
 
 #include "gemm_ffma.cuh"
 #include "gemm_generic.cuh"
+#include "gemm_mxf4.cuh"
 #include "gemm_tc.cuh"
 
 using namespace b200;
@@ -252,7 +253,8 @@ int launch_generic_requant(int m, int n, int k, const int8_t* A, int lda, const 
 int g_force_bn = 0;          // test/tuning hook (b200_gemm_debug_set_bn): 0 = heuristic
 int g_group_rows = 0;         // tuning hook: rows per raster group of the tensor-core kernels (0 = 2048)
 int g_force_cg = 0;           // test/tuning hook (b200_gemm_debug_set_cta_group): 0 = auto, 1, 2
-int g_epi8 = 0;               // tuning hook (b200_gemm_debug_set_epilogue bit 1): pair kernels of the plain kinds with 8 epilogue warps
+int g_epi8 = 1;               // pair kernels of the plain kinds drain with 8 epilogue warps (tuning hook b200_gemm_debug_set_epilogue bit 1 = back to 4):
+                              // measured int8 4096^3 2.07 -> 2.32 POP/s, bf16->fp32 2304^3 692 -> 823 TFLOP/s, bit-identical results
 int g_epi_direct = 0;         // tuning hook (b200_gemm_debug_set_epilogue): 1 = direct register stores for non-folding passes
 int g_ffma_fat = -1;          // strict kernel: 1 = 128x256 fat-thread variant, 0 = 128x128, -1 = by size
 int g_ffma_halves = 1;        // strict kernel: split the tail round into half tiles (tuning hook)
@@ -319,6 +321,10 @@ int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_tota
   p.split = split;
   p.full_tiles = (split > 1 || p.halfn) ? tiles - rem : tiles;
   p.flags = t_ctx->flags + (t_ctx->flag_slot++ % 16) * 1024;
+  if (split > 1) {          // the ordering flags start from zero whatever an aborted earlier launch left behind
+    cudaError_t e = cudaMemsetAsync(p.flags, 0, 1024 * sizeof(int), st);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+  }
   const int items = p.full_tiles + (tiles - p.full_tiles) * (p.halfn ? 2 : split);
   const int units = items < units_max ? items : units_max;
   g_ktimer.begin(st);
@@ -432,7 +438,7 @@ int tc_s8_requant(int m, int n, int k, const void* A, int lda, const void* B, in
 // Workspace for the bf16 planes: cached, grow-only (no per-call cudaMalloc in steady state).  Calls
 // in split modes are serialised on this buffer by stream order; use one stream per library instance.
 // K extent accumulated inside the tensor core before folding into C (0 = whole K): [0] BF16X3, [1] BF16X2
-int g_split_chunk_k[2] = {512, 512};
+int g_split_chunk_k[3] = {512, 512, 1024};   // BF16X3, BF16X2, F16X2
 // Grows the device's split workspace to `need` bytes.  Starts at 256 MiB (every size of the reference's
 // 256..4096 sweep fits: its harness averages the first, cold call into each row, and a cudaFree +
 // cudaMalloc there costs tens of ms) and at least doubles.  Growth synchronises the device (other
@@ -551,7 +557,7 @@ int launch_f16_split_rows(const float* A, long long lda, int rows, int cols, flo
 // another buffer to clear on the way (the idle half of the double-buffered maxima), or null.
 int launch_f16_split_cols(const float* B, long long ldb, int rows, int cols, float* cmax, uint16_t* planes,
                           long long pitch, int plane_rows, float* zero_buf, int zero_n, cudaStream_t st) {
-  col_absmax_kernel<<<dim3((cols + 127) / 128, (rows + 127) / 128), 256, 0, st>>>(B, ldb, rows, cols,
+  col_absmax_kernel<<<dim3((cols + 1023) / 1024, (rows + 31) / 32), 256, 0, st>>>(B, ldb, rows, cols,
                                                                                   reinterpret_cast<unsigned int*>(cmax));
   const int gx = (int)((pitch + 2047) / 2048);
   int gy = (t_ctx->sms * 8 + gx - 1) / gx;
@@ -572,19 +578,19 @@ int gemm_f16x2_core(int m, int n, int k, const F16Operand& a, const F16Operand& 
   if (use_pair(m, n))
     return launch_tc<KIND_FP16, 256, 6, float, ProdX2, 64, 2>(m, n, k, a.planes, a.pitch, NP * a.plane_rows, a.plane_rows,
                                                               b.planes, b.pitch, NP * b.plane_rows, b.plane_rows, C, ldc, st,
-                                                              "tc_f16x2_2cta_256x256", g_split_chunk_k[1], a.maxv, b.maxv, acc);
+                                                              "tc_f16x2_2cta_256x256", g_split_chunk_k[2], a.maxv, b.maxv, acc);
   const int bn = pick_bn(m, n, true);
   if (bn == 256)
     return launch_tc<KIND_FP16, 256, 4, float, ProdX2, 64>(m, n, k, a.planes, a.pitch, NP * a.plane_rows, a.plane_rows,
                                                            b.planes, b.pitch, NP * b.plane_rows, b.plane_rows, C, ldc, st,
-                                                           "tc_f16x2_128x256", g_split_chunk_k[1], a.maxv, b.maxv, acc);
+                                                           "tc_f16x2_128x256", g_split_chunk_k[2], a.maxv, b.maxv, acc);
   if (bn == 192)
     return launch_tc<KIND_FP16, 192, 4, float, ProdX2, 64>(m, n, k, a.planes, a.pitch, NP * a.plane_rows, a.plane_rows,
                                                            b.planes, b.pitch, NP * b.plane_rows, b.plane_rows, C, ldc, st,
-                                                           "tc_f16x2_128x192", g_split_chunk_k[1], a.maxv, b.maxv, acc);
+                                                           "tc_f16x2_128x192", g_split_chunk_k[2], a.maxv, b.maxv, acc);
   return launch_tc<KIND_FP16, 128, 6, float, ProdX2, 64>(m, n, k, a.planes, a.pitch, NP * a.plane_rows, a.plane_rows,
                                                          b.planes, b.pitch, NP * b.plane_rows, b.plane_rows, C, ldc, st,
-                                                         "tc_f16x2_128x128", g_split_chunk_k[1], a.maxv, b.maxv, acc);
+                                                         "tc_f16x2_128x128", g_split_chunk_k[2], a.maxv, b.maxv, acc);
 }
 
 // Column maxima are double-buffered outside the grow-only workspace: call i accumulates into half i % 2
@@ -741,6 +747,10 @@ int gemm_f32_impl(int m, int n, int k, const float* dA, int lda, const float* dB
   // TFLOP/s at 512^3, 2.0 vs 2.0 at 256^3) and bit-exact against the reference oracle.  From 640^3 the
   // tensor-core path pulls away (19.2 vs 15.0; 63.0 vs 41.0 at 1024^3).
   if (was_auto && (mode == B200_F32_BF16X3 || mode == B200_F32_F16X2) && tma && (double)m * n * k <= 2.0e8) mode = B200_F32_STRICT;
+  // AUTO between ~640^3 and ~1440^3: the two-launch BF16X3 path (one fused split + GEMM) beats the four-launch
+  // F16X2 path while launches, not tensor work, dominate (measured in bench.py's sweep: 1024^3 63 vs 48 TFLOP/s,
+  // 1536^3 159 vs 154, 1792^3 175 vs 205).  Both are fp32-class.
+  else if (was_auto && mode == B200_F32_F16X2 && (double)m * n * k < 3.0e9) mode = B200_F32_BF16X3;
   switch (mode) {
     case B200_F32_STRICT:
       // 128x256 fat-thread tiles once they fill most of the machine (measured at N = 4096 / 3072 / 2048:
@@ -793,10 +803,10 @@ void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes) { g_dbg_b_lbo = lb
 void b200_gemm_debug_set_bn(int bn) { g_force_bn = bn; }
 void b200_gemm_debug_set_cta_group(int cg) { g_force_cg = cg; }
 void b200_gemm_debug_set_split_tail(int on) { g_split_tail = on; }
-void b200_gemm_debug_set_epilogue(int v) { g_epi_direct = v & 1; g_epi8 = (v >> 1) & 1; }
+void b200_gemm_debug_set_epilogue(int v) { g_epi_direct = v & 1; g_epi8 = ((v >> 1) & 1) ^ 1; }
 void b200_gemm_debug_set_group_rows(int rows) { g_group_rows = rows; }
 void b200_gemm_debug_set_ffma_variant(int v) { g_ffma_halves = v & 1; g_ffma_fat = v < 0 ? -1 : (v >> 1) & 1; }
-void b200_gemm_debug_set_split_chunk(int x3_k, int x2_k) { g_split_chunk_k[0] = x3_k; g_split_chunk_k[1] = x2_k; }
+void b200_gemm_debug_set_split_chunk(int x3_k, int x2_k) { g_split_chunk_k[0] = x3_k; g_split_chunk_k[1] = x2_k; g_split_chunk_k[2] = x2_k; }
 void b200_gemm_debug_kernel_timing(int enable) { g_ktimer.on = enable != 0; g_ktimer.n = 0; }
 int b200_gemm_debug_kernel_time_ms(double* sum_ms) {
   double sum = 0;
@@ -810,6 +820,24 @@ int b200_gemm_debug_kernel_time_ms(double* sum_ms) {
   g_ktimer.n = 0;
   if (sum_ms) *sum_ms = sum;
   return cnt;
+}
+
+// Grows the split-precision workspace of the current device up front, so that no later compute call
+// synchronises or allocates (first use and growth otherwise do: cudaMalloc of the plane buffers).
+int b200_gemm_reserve_workspace(size_t bytes) {
+  int rc = ensure_device();
+  if (rc) return rc;
+  std::lock_guard<std::mutex> wlk(t_ctx->ws_mu);
+  return split_ws_reserve(bytes);
+}
+// Bytes b200_gemm_f32 needs for an m x n x k product in `precision_mode` (0 for modes without a split).
+size_t b200_gemm_workspace_bytes(int m, int n, int k, int precision_mode) {
+  const int mode = resolve_f32_mode(precision_mode);
+  const int np = mode == B200_F32_BF16X3 ? 3 : (mode == B200_F32_BF16X2 || mode == B200_F32_F16X2) ? 2 : 0;
+  if (!np || m <= 0 || n <= 0 || k <= 0) return 0;
+  const size_t a = ((size_t)np * m * plane_pitch(k) * 2 + 1023) & ~(size_t)1023;
+  const size_t b = ((size_t)np * b_plane_rows(k) * plane_pitch(n) * 2 + 1023) & ~(size_t)1023;
+  return a + b + (size_t)m * 4 + 1024;
 }
 
 int b200_gemm_f32(int m, int n, int k, const float* dA, int lda, const float* dB, int ldb, float* dC,
@@ -1028,6 +1056,72 @@ int b200_gemm_s8s8_requant(int m, int n, int k, const int8_t* dA, int lda, const
   if (k == 0 || !tma_ok(dA, lda, dB, ldb, 1))         // K = 0: every element is requant(0) = sat(round(bias))
     return launch_generic_requant(m, n, k, dA, lda, dB, ldb, dC, ldc, dScales, dBias, st);
   return tc_s8_requant(m, n, k, dA, lda, dB, ldb, dC, ldc, dScales, dBias, st);
+}
+
+// ---- the 4-bit path: block-scaled MXFP4 (the reference's cuda-int4 is "WIP") ----------------
+size_t b200_mxf4_q_bytes(int rows, int k) { return rows <= 0 || k <= 0 ? 0 : (size_t)rows * (size_t)(((k + 127) & ~127) / 2); }
+size_t b200_mxf4_sf_bytes(int rows, int k) {
+  return rows <= 0 || k <= 0 ? 0 : (size_t)((rows + 127) / 128) * (size_t)((k + 127) / 128) * 512;
+}
+
+int b200_mxf4_quantize_a(int m, int k, const float* dA, int lda, uint8_t* dQ, uint8_t* dSF, void* stream) {
+  if (m <= 0 || k <= 0 || !dA || !dQ || !dSF || lda < k) return B200_ERR_BAD_ARG;
+  int rc = ensure_device();
+  if (rc) return rc;
+  const int kpad = (k + 127) & ~127, rows_pad = (m + 127) & ~127;
+  const long long total = (long long)rows_pad * (kpad / 32);
+  long long blocks = (total + 255) / 256;
+  if (blocks > t_ctx->sms * 16) blocks = t_ctx->sms * 16;
+  mxf4_quantize_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dA, lda, m, k, dQ, kpad, dSF, rows_pad);
+  g_launches++;
+  t_last_kernel = "mxf4_quantize_rows";
+  return last_launch_status();
+}
+
+// B is k x n row-major; the output is B^T quantised along K: n rows of kpad/2 bytes (the K-major operand the
+// 4-bit tensor path requires) + scale atoms indexed by (n, K-block).
+int b200_mxf4_quantize_b(int k, int n, const float* dB, int ldb, uint8_t* dQ, uint8_t* dSF, void* stream) {
+  if (n <= 0 || k <= 0 || !dB || !dQ || !dSF || ldb < n) return B200_ERR_BAD_ARG;
+  int rc = ensure_device();
+  if (rc) return rc;
+  const int kpad = (k + 127) & ~127, n_pad = (n + 127) & ~127;
+  mxf4_quantize_cols_t_kernel<<<dim3((n_pad + 255) / 256, kpad / 32), 256, 0, (cudaStream_t)stream>>>(dB, ldb, k, n, dQ, kpad, dSF, n_pad);
+  g_launches++;
+  t_last_kernel = "mxf4_quantize_cols_t";
+  return last_launch_status();
+}
+
+int b200_gemm_mxf4(int m, int n, int k, const uint8_t* dAq, const uint8_t* dSFA, const uint8_t* dBq, const uint8_t* dSFB,
+                   float* dC, int ldc, void* stream) {
+  if (m < 0 || n < 0 || k < 0) return B200_ERR_BAD_ARG;
+  if (m == 0 || n == 0) return 0;
+  if (!dC || ldc < n) return B200_ERR_BAD_ARG;
+  int rc = ensure_device();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k == 0) return launch_zero<float>(m, n, dC, ldc, st);
+  if (!dAq || !dSFA || !dBq || !dSFB || !aligned16(dAq) || !aligned16(dBq) || !aligned16(dSFA) || !aligned16(dSFB)) return B200_ERR_BAD_ARG;
+  using Cfg = Mxf4Cfg<128>;
+  const int kpad = (k + 127) & ~127;
+  CUtensorMap tmA, tmB;
+  rc = get_map(&tmA, dAq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, kpad / 2, m, kpad / 2, 128, Cfg::BM, 1);
+  if (rc) return rc;
+  rc = get_map(&tmB, dBq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, kpad / 2, n, kpad / 2, 128, 128, 1);
+  if (rc) return rc;
+  Mxf4Params p;
+  p.C = dC; p.ldc = ldc; p.M = m; p.N = n; p.K = kpad;
+  p.sfa = dSFA; p.sfb = dSFB;
+  p.tiles_m = (m + 127) / 128; p.tiles_n = (n + 127) / 128;
+  p.vec_ok = aligned16(dC) && (ldc % 4) == 0;
+  auto kern = gemm_mxf4_kernel<128>;
+  if (int arc = ensure_smem_attr(kern, Cfg::SMEM_BYTES)) return arc;
+  const int tiles = p.tiles_m * p.tiles_n;
+  g_ktimer.begin(st);
+  kern<<<tiles < t_ctx->sms ? tiles : t_ctx->sms, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  g_ktimer.end(st);
+  g_launches++;
+  t_last_kernel = "tc_mxf4_128x128";
+  return last_launch_status();
 }
 
 int b200_convert_f32_to_bf16(const float* dSrc, uint16_t* dDst, size_t count, void* stream) {

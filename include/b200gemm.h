@@ -26,8 +26,9 @@
  *
  * Device entry points are fully asynchronous on `stream` (a cudaStream_t passed
  * as void*; NULL = the legacy default stream the reference harness uses,
- * cuda/test_MMult.cpp:98-110), never synchronise, never allocate per call and
- * are re-entrant on one stream.  They return 0 on success or a cudaError_t /
+ * cuda/test_MMult.cpp:98-110), never synchronise or allocate in steady state (see
+ * b200_gemm_reserve_workspace for the first call) and may be called on any stream of any
+ * sm_100 device (per-device state; make the device current on the calling thread).  They return 0 on success or a cudaError_t /
  * negative B200_ERR_* code.  There is NO CPU fallback: without a CUDA device of
  * compute capability 10.x every compute entry point returns
  * B200_ERR_NO_DEVICE.
@@ -94,6 +95,15 @@ const char* b200_gemm_last_kernel(void);
 unsigned long long b200_gemm_launch_count(void);
 int  b200_gemm_default_f32_mode(void);
 void b200_gemm_set_default_f32_mode(int mode);
+
+/* The split-precision fp32 modes keep the planes of A and B in a per-device, grow-only workspace.  Its first
+ * use and every growth allocate (and synchronise the device); steady-state calls never do.  Reserve it up front
+ * — b200_gemm_reserve_workspace(b200_gemm_workspace_bytes(m, n, k, mode)) on the device that will run the
+ * calls — to keep even the first call allocation-free (e.g. ahead of CUDA-graph capture).  State is per device:
+ * one process may drive several GPUs (make the device current on the calling thread); calls on different
+ * streams of one device are serialised on the workspace by an event, not by the host. */
+size_t b200_gemm_workspace_bytes(int m, int n, int k, int precision_mode);
+int    b200_gemm_reserve_workspace(size_t bytes);
 
 /* fp32: C = A*B.  Replaces MY_MMult(cublasHandle_t,m,n,k,dA,lda,dB,ldb,dC,ldc)
  * (cuda/test_MMult.cpp:13-14,100-103).  DEVICE pointers. */
@@ -225,6 +235,25 @@ int  b200_gemm_f32_rowpanel_host(b200_rowpanel* plan, int m_local, int n, int k,
                                  const float* A_local, int lda, const float* B, int ldb,
                                  float* C_local, int ldc, int root);
 
+/* ---- the 4-bit path ------------------------------------------------------------------
+ * The reference lists a cuda-int4 back-end and ships only the word "WIP" (cuda-int4/README.md:1;
+ * README.md:13-15,118-120), so there is no interface to mirror: this is the chgemm idea (quantised operands,
+ * wide accumulate) on Blackwell's only 4-bit tensor type, OCP MXFP4 — E2M1 elements with one power-of-two
+ * UE8M0 scale per 32 consecutive K elements (tcgen05.mma.kind::mxf4.block_scale), fp32 accumulate and output.
+ *   quantize_a   A (m x k fp32, row-major)  -> dQ (m rows of kpad/2 bytes, two elements per byte, low nibble
+ *                first; kpad = k rounded up to 128) + dSF (scale atoms, b200_mxf4_sf_bytes(m, k) bytes)
+ *   quantize_b   B (k x n fp32, row-major)  -> B^T quantised along K: dQ has n rows (4-bit operands must be
+ *                K-major for the tensor core: the one transposing pass of this library) + dSF(n, k)
+ *   gemm_mxf4    C (m x n fp32) = dequant(A) * dequant(B)
+ * Scale atom layout: [rows/128][kpad/128][512 bytes], byte (r%32)*16 + ((r/32)%4)*4 + (kblock%4).
+ * DEVICE pointers, 16-byte aligned; asynchronous on `stream`. */
+size_t b200_mxf4_q_bytes(int rows, int k);
+size_t b200_mxf4_sf_bytes(int rows, int k);
+int b200_mxf4_quantize_a(int m, int k, const float* dA, int lda, uint8_t* dQ, uint8_t* dSF, void* stream);
+int b200_mxf4_quantize_b(int k, int n, const float* dB, int ldb, uint8_t* dQ, uint8_t* dSF, void* stream);
+int b200_gemm_mxf4(int m, int n, int k, const uint8_t* dAq, const uint8_t* dSFA,
+                   const uint8_t* dBq, const uint8_t* dSFB, float* dC, int ldc, void* stream);
+
 /* Element-wise helper the bf16 config needs on the device: round-to-nearest-
  * even fp32 -> bf16 (the rounding SURVEY §8d prescribes for config 3 inputs). */
 int b200_convert_f32_to_bf16(const float* dSrc, uint16_t* dDst, size_t count,
@@ -249,9 +278,11 @@ void b200_gemm_debug_set_group_rows(int rows);
 /* Tuning hook for the strict fp32 kernels: bit 0 = half tiles in the last partial round (default on),
  * bit 1 = force the 128x256 fat-thread kernel; a negative value restores selection by size. */
 void b200_gemm_debug_set_ffma_variant(int v);
-/* Tuning hook: 1 = non-folding epilogue passes store straight from registers instead of through the
- * shared-memory transpose (measured no faster on B200; default 0). */
-void b200_gemm_debug_set_epilogue(int direct);
+/* Tuning hook, bit mask: bit 0 = non-folding epilogue passes store straight from registers instead of through
+ * the shared-memory transpose (measured no faster on B200; default off); bit 1 = drain the CTA-pair kernels of
+ * the plain kinds (bf16, tf32, int8) with 4 epilogue warps instead of the default 8 (two warps per TMEM lane
+ * quadrant, half the column passes each; results are bit-identical). */
+void b200_gemm_debug_set_epilogue(int mask);
 /* Measurement hook: while enabled, a CUDA-event pair is recorded on the launching stream around
  * every dominant GEMM kernel launch (not the split pre-pass).  b200_gemm_debug_kernel_time_ms
  * synchronises those events, stores the summed kernel time and returns the number of launches

@@ -279,3 +279,89 @@ float oracle_bf16_to_f32(uint16_t h) {
 void oracle_round_to_bf16_inplace(size_t count, float* a) {
   for (size_t i = 0; i < count; i++) a[i] = oracle_bf16_to_f32(oracle_f32_to_bf16(a[i]));
 }
+
+/* ---- MXFP4 (the 4-bit path; parity UNPINNED: the reference ships only "WIP", cuda-int4/README.md:1) --------
+ * Restates the published OCP Microscaling Formats (MX) v1.0 specification: E2M1 elements
+ * {0, .5, 1, 1.5, 2, 3, 4, 6} with sign, one UE8M0 scale 2^(e-127) per 32 consecutive elements,
+ * shared exponent = floor(log2(max|x|)) - emax_elem (emax_elem = 2), elements rounded to nearest even and
+ * saturated.  Nothing in /root/reference can pin this; the GPU path is checked against THIS restatement. */
+static const float k_e2m1[8] = {0.f, .5f, 1.f, 1.5f, 2.f, 3.f, 4.f, 6.f};
+uint8_t oracle_e2m1_encode(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  if (v != v) return 0;
+  float a = fabsf(v);
+  uint8_t code = a <= 0.25f ? 0 : a < 0.75f ? 1 : a <= 1.25f ? 2 : a < 1.75f ? 3 : a <= 2.5f ? 4 : a < 3.5f ? 5 : a <= 5.0f ? 6 : 7;
+  return (uint8_t)(((u >> 31) << 3) | code);
+}
+float oracle_e2m1_decode(uint8_t c) { return (c & 8) ? -k_e2m1[c & 7] : k_e2m1[c & 7]; }
+uint8_t oracle_ue8m0_from_max(float mx) {
+  uint32_t u;
+  memcpy(&u, &mx, 4);
+  int ef = (int)((u >> 23) & 0xFF);
+  if (ef == 255) return 255;
+  int e = ef - 2;
+  return (uint8_t)(e < 0 ? 0 : e);
+}
+double oracle_ue8m0_value(uint8_t e) { return e == 255 ? NAN : ldexp(1.0, (int)e - 127); }
+/* rows x cols fp32 -> q (rows x kpad/2 bytes, element 2i in the low nibble) + sf (rows x kpad/32, plain row-major);
+ * kpad = cols rounded up to 128, padding elements are zero. */
+void oracle_mxf4_quantize(int rows, int cols, const float* src, int ld, uint8_t* q, uint8_t* sf) {
+  int kpad = (cols + 127) & ~127, kblocks = kpad / 32;
+  for (int r = 0; r < rows; r++)
+    for (int kb = 0; kb < kblocks; kb++) {
+      float x[32], mx = 0.f;
+      for (int e = 0; e < 32; e++) {
+        int c = kb * 32 + e;
+        x[e] = c < cols ? src[(size_t)r * ld + c] : 0.f;
+        if (fabsf(x[e]) > mx) mx = fabsf(x[e]);
+      }
+      uint8_t se = oracle_ue8m0_from_max(mx);
+      int xe = 254 - (int)se;                               /* 2^-(se-127), clamped to normal floats like the device code */
+      xe = xe < 1 ? 1 : (xe > 254 ? 254 : xe);
+      uint32_t ib = (uint32_t)xe << 23;
+      float inv;
+      memcpy(&inv, &ib, 4);
+      sf[(size_t)r * kblocks + kb] = se;
+      for (int e = 0; e < 32; e += 2)
+        q[(size_t)r * (kpad / 2) + kb * 16 + e / 2] =
+            (uint8_t)(oracle_e2m1_encode(x[e] * inv) | (oracle_e2m1_encode(x[e + 1] * inv) << 4));
+    }
+}
+/* plain scales (rows x kblocks) -> the 512-byte atom layout the tensor core's scale copy consumes
+ * ([rows_pad/128][kpad/128][512]; byte (r%32)*16 + ((r/32)%4)*4 + kb%4); padding rows get scale 0. */
+void oracle_mxf4_sf_to_atoms(int rows, int kpad, const uint8_t* sf, uint8_t* atoms) {
+  int kblocks = kpad / 32, katoms = kpad / 128, rows_pad = (rows + 127) & ~127;
+  memset(atoms, 0, (size_t)(rows_pad / 128) * katoms * 512);
+  for (int r = 0; r < rows; r++)
+    for (int kb = 0; kb < kblocks; kb++)
+      atoms[((size_t)(r >> 7) * katoms + (kb >> 2)) * 512 + (size_t)(r & 31) * 16 + ((r >> 5) & 3) * 4 + (kb & 3)] =
+          sf[(size_t)r * kblocks + kb];
+}
+/* C[m x n] = sum_k dq(A)[m,k] * dq(B^T)[n,k] in double: qa (m x kpad/2), qb (n x kpad/2), plain scales. */
+typedef struct { int n, kpad; const uint8_t *qa, *sa, *qb, *sb; double* c; } mx_ctx;
+static void rows_mxf4(int i0, int i1, void* vc) {
+  mx_ctx* x = (mx_ctx*)vc;
+  int kblocks = x->kpad / 32;
+  for (int i = i0; i < i1; i++)
+    for (int j = 0; j < x->n; j++) {
+      double acc = 0.0;
+      for (int kb = 0; kb < kblocks; kb++) {
+        double s = oracle_ue8m0_value(x->sa[(size_t)i * kblocks + kb]) * oracle_ue8m0_value(x->sb[(size_t)j * kblocks + kb]);
+        double part = 0.0;
+        for (int e = 0; e < 16; e++) {
+          uint8_t ba = x->qa[(size_t)i * (x->kpad / 2) + kb * 16 + e], bb = x->qb[(size_t)j * (x->kpad / 2) + kb * 16 + e];
+          part += (double)oracle_e2m1_decode(ba & 15) * oracle_e2m1_decode(bb & 15) +
+                  (double)oracle_e2m1_decode(ba >> 4) * oracle_e2m1_decode(bb >> 4);
+        }
+        acc += part * s;
+      }
+      x->c[(size_t)i * x->n + j] = acc;
+    }
+}
+void oracle_mxf4_gemm(int m, int n, int kpad, const uint8_t* qa, const uint8_t* sa, const uint8_t* qb, const uint8_t* sb,
+                      double* c) {
+  mx_ctx x = {n, kpad, qa, sa, qb, sb, c};
+  par_rows(m, rows_mxf4, &x);
+}
+

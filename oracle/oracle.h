@@ -98,6 +98,16 @@ uint16_t oracle_f32_to_bf16(float x);
 float    oracle_bf16_to_f32(uint16_t h);
 void     oracle_round_to_bf16_inplace(size_t count, float* a);
 
+/* ---- MXFP4 (4-bit path): OCP MX v1.0 restated; parity UNPINNED (reference: cuda-int4/README.md:1 "WIP") ---- */
+uint8_t oracle_e2m1_encode(float v);
+float   oracle_e2m1_decode(uint8_t code);
+uint8_t oracle_ue8m0_from_max(float max_abs);
+double  oracle_ue8m0_value(uint8_t e);
+void    oracle_mxf4_quantize(int rows, int cols, const float* src, int ld, uint8_t* q, uint8_t* sf);
+void    oracle_mxf4_sf_to_atoms(int rows, int kpad, const uint8_t* sf, uint8_t* atoms);
+void    oracle_mxf4_gemm(int m, int n, int kpad, const uint8_t* qa, const uint8_t* sa, const uint8_t* qb,
+                         const uint8_t* sb, double* c);
+
 #ifdef __cplusplus
 }
 #endif

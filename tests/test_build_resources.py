@@ -10,6 +10,9 @@ LOG = os.path.join(_libs.ROOT, _libs.PKG, "build_ptxas.log")
 
 
 def kernels():
+    if not os.path.exists(LOG):      # the log is a build product (git-ignored): regenerate it with the library
+        import subprocess
+        subprocess.check_call(["make", "-B", "-C", os.path.join(_libs.ROOT, _libs.PKG), "libb200gemm.so"])
     out, name = {}, None
     for line in open(LOG):
         m = re.search(r"Compiling entry function '(\w+)' for 'sm_100a'", line)
@@ -31,10 +34,14 @@ def test_log_covers_every_kernel_family():
 
 
 def test_tensor_core_kernels_do_not_spill():
-    # 192 threads, one CTA per SM: up to 255 registers are free, a spill would sit in the epilogue's inner loop
+    # one CTA per SM.  192 threads (4 epilogue warps): up to 255 registers; 320 threads (8 epilogue warps): 204;
+    # split-precision kernels (384 threads, setmaxnreg 88 / 208 after a 168-register launch): the running sum of a
+    # tile lives in the epilogue warps' registers — a spill there would sit in the per-chunk add loop
     for n, v in kernels().items():
         if "gemm_tc_kernel" in n:
             assert v["spill"] == 0 and v["regs"] <= 255, (n, v)
+            if "ProdX" in n:
+                assert v["regs"] <= 168, (n, v)
 
 
 def test_strict_kernels_keep_their_occupancy():
@@ -48,5 +55,7 @@ def test_strict_kernels_keep_their_occupancy():
 
 def test_prepass_kernels_allow_full_occupancy():
     for n, v in kernels().items():
-        if "split_planes_kernel" in n:
+        if "split_planes_kernel" in n or "split_f16_cols_kernel" in n or "col_absmax_kernel" in n:
             assert v["regs"] <= 64 and v["spill"] == 0, (n, v)      # 8 blocks of 256 threads per SM
+        if "split_f16_rows_kernel" in n:
+            assert v["spill"] == 0, (n, v)                          # register-resident rows: no local memory

@@ -236,7 +236,7 @@ def test_full_size_s8_requant_4096(gemm, oracle):
     a, b, scales, bias = _rq_case(oracle, N, N, N, 81, "layer")
     A, B, S, Bi = cuda(a), cuda(b), cuda(scales), cuda(bias)
     out = gemm.gemm_s8s8_requant(A, B, S, Bi)
-    assert gemm.last_kernel() == "tc_s8_requant_2cta_256x256"
+    assert gemm.last_kernel().startswith("tc_s8_requant_2cta_256x256")
     rows = np.arange(0, N, 31)[:128]
     ref = _libs.requant_s8(oracle, _libs.ref_s8(oracle, a[rows], b), scales[rows], bias[rows])
     assert np.array_equal(out[torch.from_numpy(rows).cuda()].cpu().numpy(), ref)

@@ -47,7 +47,7 @@ for n in (4096, 8192, 2304):
         "s8 requant": lambda i: g.gemm_s8s8_requant(i8[i % R][0], i8[i % R][1], sc, bi, out=o8[i % R]),
     }
     ref = {}
-    for hook in (0, 2):
+    for hook in (2, 0):        # bit 1 set = 4 epilogue warps (the default is 8)
         g.lib.b200_gemm_debug_set_epilogue(hook)
         for name, fn in cases.items():
             ms = timeit(fn)
@@ -56,11 +56,11 @@ for n in (4096, 8192, 2304):
             outt = {"bf16->bf16": ob, "bf16->f32": of, "tf32": of, "s8->s32": oi, "s8 requant": o8}[name][0]
             key = (name, n)
             same = None
-            if hook == 0:
+            if hook == 2:
                 ref[key] = outt.clone()
             else:
                 same = bool(torch.equal(ref[key], outt))
-            res.append({"n": n, "case": name, "epi_warps": 8 if hook else 4, "ms": ms, "tops": 2.0 * n ** 3 / ms / 1e9,
+            res.append({"n": n, "case": name, "epi_warps": 4 if hook else 8, "ms": ms, "tops": 2.0 * n ** 3 / ms / 1e9,
                         "kernel": g.last_kernel(), "identical_to_4_warp": same})
             print(res[-1], flush=True)
     g.lib.b200_gemm_debug_set_epilogue(0)

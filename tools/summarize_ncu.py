@@ -85,6 +85,12 @@ def main():
         path = os.path.join(ROOT, "profiles", f"{rnd}_{name}.txt")
         open(path, "w").write("\n".join(lines) + "\n")
         print("wrote", path)
+    try:
+        head = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    except Exception:
+        head = "?"
+    traffic["_source"] = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of tools/run_one.py, "
+                          f"summarised by tools/summarize_ncu.py; last updated {rnd} on top of git {head} (not measured inside bench.py)")
     json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
 
 
