@@ -26,12 +26,12 @@ EXPORTS = [
     "b200_mxf4_quantize_a", "b200_mxf4_quantize_b", "b200_gemm_mxf4", "b200_gemm_f32_host", "b200_gemm_bf16", "b200_gemm_s8s32",
     "b200_gemm_s8s32_host", "b200_gemm_s8s8_requant", "b200_gemm_f32_pack_b", "b200_gemm_f32_packed",
     "b200_gemm_f32_pack_free", "b200_nccl_load", "b200_nccl_last_error", "b200_comm_unique_id", "b200_comm_init_rank",
-    "b200_comm_destroy", "b200_rowpanel_create", "b200_rowpanel_destroy", "b200_rowpanel_slices", "b200_gemm_f32_rowpanel",
+    "b200_comm_destroy", "b200_rowpanel_create", "b200_rowpanel_destroy", "b200_rowpanel_slices", "b200_rowpanel_set_reserve_sms", "b200_rowpanel_trace", "b200_rowpanel_trace_dump", "b200_gemm_f32_rowpanel",
     "b200_gemm_f32_rowpanel_host", "b200_gemm_f32_pack_a", "b200_gemm_f32_packed_ab", "b200_gemm_f32_pack_free_a",
     "b200_convert_f32_to_bf16", "b200_gemm_debug_set_b_desc", "b200_gemm_debug_set_bn",
     "b200_gemm_debug_set_split_chunk", "b200_gemm_debug_kernel_timing", "b200_gemm_debug_kernel_time_ms",
     "b200_gemm_debug_set_cta_group", "b200_gemm_debug_set_split_tail", "b200_gemm_debug_set_group_rows",
-    "b200_gemm_debug_set_ffma_variant", "b200_gemm_debug_set_epilogue",
+    "b200_gemm_debug_set_ffma_variant", "b200_gemm_debug_set_epilogue", "b200_gemm_debug_set_pdl",
 ]
 
 
@@ -87,6 +87,10 @@ lib.b200_rowpanel_create.argtypes = [C.POINTER(_vp), _vp, _i, _i, _i, _i, C.POIN
 lib.b200_rowpanel_destroy.argtypes = [_vp]
 lib.b200_rowpanel_destroy.restype = None
 lib.b200_rowpanel_slices.argtypes = [_vp, C.POINTER(_i), _i]
+lib.b200_rowpanel_set_reserve_sms.argtypes = [_vp, _i]
+lib.b200_rowpanel_trace.argtypes = [_vp, _i]
+lib.b200_rowpanel_trace.restype = None
+lib.b200_rowpanel_trace_dump.argtypes = [_vp, C.POINTER(C.c_float), _i]
 lib.b200_gemm_f32_rowpanel.argtypes = [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp]
 lib.b200_gemm_f32_rowpanel_host.argtypes = [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i]
 lib.b200_gemm_s8s8_requant.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]
@@ -98,6 +102,7 @@ lib.b200_gemm_debug_set_split_chunk.argtypes = [_i, _i]
 lib.b200_gemm_debug_kernel_timing.argtypes = [_i]
 lib.b200_gemm_debug_set_cta_group.argtypes = [_i]
 lib.b200_gemm_debug_set_split_tail.argtypes = [_i]
+lib.b200_gemm_debug_set_pdl.argtypes = [_i]
 lib.b200_gemm_debug_kernel_time_ms.argtypes = [C.POINTER(C.c_double)]
 
 

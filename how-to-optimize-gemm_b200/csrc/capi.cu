@@ -51,6 +51,10 @@ thread_local const char* t_last_kernel = "none";
 // General epilogue request of the current call (b200_gemm_f32_ex): read by launch_tc, reset by the entry point.
 struct EpiOpts { int axpby = 0; float alpha = 1.f, beta = 0.f; };
 thread_local EpiOpts t_epi;
+// SMs the tensor-core launches of the current call leave free (the row-panel plan sets it while a later K-slice
+// of B is still being broadcast: a persistent GEMM holding every SM would starve NCCL's copy kernels and
+// serialise the exchange behind the math — measured on 2 x B200).
+thread_local int t_sm_reserve = 0;
 int g_dbg_b_lbo = 0, g_dbg_b_sbo = 0;
 
 // ---- per-device state ------------------------------------------------------------------------------
@@ -221,6 +225,29 @@ int last_launch_status() {
   return 0;
 }
 
+// Launch with the programmatic-serialisation (PDL) attribute: the kernel may start while the previous kernel of
+// the stream drains; every kernel launched through here calls griddep_wait before it touches global memory.
+int g_pdl = 1;                // tuning hook (b200_gemm_debug_set_pdl)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (cluster > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    n++;
+  }
+  if (g_pdl) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    n++;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <typename T>
 int launch_zero(int m, int n, T* C, int ldc, cudaStream_t st) {
   dim3 grid((n + 255) / 256, m < 4096 ? m : 4096);
@@ -296,7 +323,7 @@ int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_tota
   auto kern = gemm_tc_kernel<KIND, BN, STAGES, OutT, Prod, A_ROW_BYTES, CG, EPIW>;
   if (int arc = ensure_smem_attr(kern, Cfg::SMEM_BYTES)) return arc;
   int tiles = p.tiles_m * p.tiles_n;
-  const int units_max = t_ctx->sms / CG;                 // CTAs, or CTA pairs (one per TPC)
+  const int units_max = (t_ctx->sms - t_sm_reserve > 2 * CG ? t_ctx->sms - t_sm_reserve : t_ctx->sms) / CG;   // CTAs, or CTA pairs (one per TPC)
   // Wave quantisation: the last, partial round of tiles (or the only round of a small problem) is
   // cut along K so that every CTA/pair has work: rem tiles x split parts <= units.
   const int num_kb = (k + Cfg::BK - 1) / Cfg::BK;
@@ -328,19 +355,8 @@ int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_tota
   const int items = p.full_tiles + (tiles - p.full_tiles) * (p.halfn ? 2 : split);
   const int units = items < units_max ? items : units_max;
   g_ktimer.begin(st);
-  if constexpr (CG == 1) {
-    kern<<<units, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(units * CG);
-    cfg.blockDim = dim3(Cfg::THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+  {
+    cudaError_t e = launch_pdl(kern, dim3(units * CG), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, CG, tmA, tmB, p);
     if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
   }
   g_ktimer.end(st);
@@ -482,7 +498,7 @@ int launch_split(const SplitJob& ja, const SplitJob& jb, int jobs, cudaStream_t 
   int gy = (t_ctx->sms * 8 + jobs * gx - 1) / (jobs * gx);        // ~8 blocks per SM over the launch
   if (gy > (tall + 1) / 2) gy = (tall + 1) / 2;
   if (gy < 1) gy = 1;
-  split_planes_kernel<NP><<<dim3(gx, gy, jobs), 256, 0, st>>>(ja, jb);
+  launch_pdl(split_planes_kernel<NP>, dim3(gx, gy, jobs), dim3(256), 0, st, 1, ja, jb);
   g_launches += 1;
   return last_launch_status();
 }
@@ -545,10 +561,10 @@ int launch_f16_split_rows(const float* A, long long lda, int rows, int cols, flo
   const int cap = t_ctx->sms * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  if (cols <= 1024) split_f16_rows_kernel<4><<<blocks, 256, 0, st>>>(A, lda, rows, cols, rmax, planes, pitch, plane_rows);
-  else if (cols <= 2048) split_f16_rows_kernel<8><<<blocks, 256, 0, st>>>(A, lda, rows, cols, rmax, planes, pitch, plane_rows);
-  else if (cols <= 4096) split_f16_rows_kernel<16><<<blocks, 256, 0, st>>>(A, lda, rows, cols, rmax, planes, pitch, plane_rows);
-  else split_f16_rows_kernel<0><<<blocks, 256, 0, st>>>(A, lda, rows, cols, rmax, planes, pitch, plane_rows);
+  if (cols <= 1024) launch_pdl(split_f16_rows_kernel<4>, dim3(blocks), dim3(256), 0, st, 1, A, (long long)lda, rows, cols, rmax, planes, pitch, plane_rows);
+  else if (cols <= 2048) launch_pdl(split_f16_rows_kernel<8>, dim3(blocks), dim3(256), 0, st, 1, A, (long long)lda, rows, cols, rmax, planes, pitch, plane_rows);
+  else if (cols <= 4096) launch_pdl(split_f16_rows_kernel<16>, dim3(blocks), dim3(256), 0, st, 1, A, (long long)lda, rows, cols, rmax, planes, pitch, plane_rows);
+  else launch_pdl(split_f16_rows_kernel<0>, dim3(blocks), dim3(256), 0, st, 1, A, (long long)lda, rows, cols, rmax, planes, pitch, plane_rows);
   g_launches++;
   return last_launch_status();
 }
@@ -557,8 +573,8 @@ int launch_f16_split_rows(const float* A, long long lda, int rows, int cols, flo
 // another buffer to clear on the way (the idle half of the double-buffered maxima), or null.
 int launch_f16_split_cols(const float* B, long long ldb, int rows, int cols, float* cmax, uint16_t* planes,
                           long long pitch, int plane_rows, float* zero_buf, int zero_n, cudaStream_t st) {
-  col_absmax_kernel<<<dim3((cols + 1023) / 1024, (rows + 31) / 32), 256, 0, st>>>(B, ldb, rows, cols,
-                                                                                  reinterpret_cast<unsigned int*>(cmax));
+  launch_pdl(col_absmax_kernel, dim3((cols + 1023) / 1024, (rows + 31) / 32), dim3(256), 0, st, 1, B, (long long)ldb, rows, cols,
+             reinterpret_cast<unsigned int*>(cmax));
   const int gx = (int)((pitch + 2047) / 2048);
   int gy = (t_ctx->sms * 8 + gx - 1) / gx;
   if (gy > (plane_rows + 1) / 2) gy = (plane_rows + 1) / 2;
@@ -567,7 +583,7 @@ int launch_f16_split_cols(const float* B, long long ldb, int rows, int cols, flo
     cudaMemsetAsync(zero_buf, 0, (size_t)zero_n * 4, st);
     zero_buf = nullptr;
   }
-  split_f16_cols_kernel<<<dim3(gx, gy), 256, 0, st>>>(B, ldb, rows, cols, cmax, planes, pitch, plane_rows, zero_buf, zero_n);
+  launch_pdl(split_f16_cols_kernel, dim3(gx, gy), dim3(256), 0, st, 1, B, (long long)ldb, rows, cols, (const float*)cmax, planes, pitch, plane_rows, zero_buf, zero_n);
   g_launches += 2;
   return last_launch_status();
 }
@@ -801,6 +817,7 @@ void b200_gemm_set_default_f32_mode(int mode) {
 }
 void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes) { g_dbg_b_lbo = lbo_bytes; g_dbg_b_sbo = sbo_bytes; }
 void b200_gemm_debug_set_bn(int bn) { g_force_bn = bn; }
+void b200_gemm_debug_set_pdl(int on) { g_pdl = on != 0; }
 void b200_gemm_debug_set_cta_group(int cg) { g_force_cg = cg; }
 void b200_gemm_debug_set_split_tail(int on) { g_split_tail = on; }
 void b200_gemm_debug_set_epilogue(int v) { g_epi_direct = v & 1; g_epi8 = ((v >> 1) & 1) ^ 1; }

@@ -273,6 +273,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if constexpr (CG == 2) cluster_sync(); else __syncthreads();   // peers touch each other's barriers
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (s_tmem_ptr - smem_base));
+  // PDL: everything above (barriers, TMEM, descriptor prefetch) may overlap the tail of the previous kernel in
+  // the stream; nothing below (operand loads, C stores) may.
+  griddep_launch();
+  griddep_wait();
 
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int num_items = p.full_tiles + (num_tiles - p.full_tiles) * (p.halfn ? 2 : p.split);
@@ -773,6 +777,8 @@ struct SplitJob {
 // a time so that 64 B of loads are in flight per thread; HBM-bound: 4 + 2*NP bytes per element.
 template <int NP>
 __global__ void __launch_bounds__(256) split_planes_kernel(const SplitJob ja, const SplitJob jb) {
+  griddep_launch();
+  griddep_wait();
   const SplitJob& jo = blockIdx.z == 0 ? ja : jb;
   const float* __restrict__ src = jo.src;
   uint16_t* __restrict__ dst = jo.dst;
@@ -863,6 +869,8 @@ template <int VPL>
 __global__ void __launch_bounds__(256) split_f16_rows_kernel(const float* __restrict__ src, long long ld, int rows,
                                                              int cols, float* __restrict__ rmax,
                                                              uint16_t* __restrict__ dst, long long dld, int plane_rows) {
+  griddep_launch();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
@@ -955,6 +963,8 @@ __global__ void __launch_bounds__(256) split_f16_rows_kernel(const float* __rest
 __global__ void __launch_bounds__(256) col_absmax_kernel(const float* __restrict__ src, long long ld, int rows,
                                                          int cols, unsigned int* __restrict__ out) {
   constexpr int ROWS = 32;
+  griddep_launch();
+  griddep_wait();
   const int c = blockIdx.x * 1024 + threadIdx.x * 4;
   if (c >= cols) return;
   const int r0 = blockIdx.y * ROWS, r1 = min(r0 + ROWS, rows);
@@ -989,6 +999,8 @@ __global__ void __launch_bounds__(256) split_f16_cols_kernel(const float* __rest
                                                              int cols, const float* __restrict__ cmax,
                                                              uint16_t* __restrict__ dst, long long dld, int plane_rows,
                                                              float* __restrict__ zero_buf, int zero_n) {
+  griddep_launch();
+  griddep_wait();
   const int c = (int)(blockIdx.x * 256 + threadIdx.x) * 8;
   if (blockIdx.y == 0 && zero_buf != nullptr) {
 #pragma unroll

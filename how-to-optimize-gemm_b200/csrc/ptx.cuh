@@ -255,6 +255,14 @@ __device__ __forceinline__ int32_t requant_s8(int32_t acc, float scale, float bi
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
+// Programmatic dependent launch: launch_dependents lets the next kernel in the stream (if it was launched with
+// the programmatic-serialisation attribute) start its own prologue once every CTA of this grid has got here;
+// griddep_wait blocks until the grid this one depends on has completed and its memory is visible.  Both are
+// no-ops for launches without the attribute.  Every kernel launched with the attribute calls griddep_wait
+// before its first global-memory access.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));

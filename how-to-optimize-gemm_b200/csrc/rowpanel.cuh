@@ -65,6 +65,9 @@ struct b200_rowpanel {
   int rank = 0, world = 1, dev = -1;
   int m_max = 0, n = 0, k = 0, mode = 0;
   int nslices = 0;
+  int trace = 0;            // diagnostics: timing events around every stage of the last call (b200_rowpanel_trace)
+  cudaEvent_t tr[8 + 6 * kMaxSlices] = {};
+  int reserve_sms = 16;     // SMs the GEMMs of all but the last K-slice leave to the exchange's copy kernels
   int k0[kMaxSlices + 1] = {};
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_b[kMaxSlices] = {}, ev_done = nullptr;
@@ -91,6 +94,7 @@ void rowpanel_free(b200_rowpanel* rp) {
   if (rp->hC) cudaFree(rp->hC);
   if (rp->hpb) { pack_release(rp->hpb); delete rp->hpb; }
   for (int j = 0; j < kMaxSlices; j++) { if (rp->ev_b[j]) cudaEventDestroy(rp->ev_b[j]); if (rp->ev_hb[j]) cudaEventDestroy(rp->ev_hb[j]); }
+  for (auto& e : rp->tr) if (e) cudaEventDestroy(e);
   for (int j = 0; j < 8; j++) { if (rp->ev_in[j]) cudaEventDestroy(rp->ev_in[j]); if (rp->ev_out[j]) cudaEventDestroy(rp->ev_out[j]); }
   if (rp->ev_start) cudaEventDestroy(rp->ev_start);
   if (rp->ev_done) cudaEventDestroy(rp->ev_done);
@@ -102,6 +106,14 @@ void rowpanel_free(b200_rowpanel* rp) {
   delete rp;
 }
 
+// trace slots: 0 start(st) 1 after A split(st); per slice j: 8+6j+{0: bcast begin(comm), 1: bcast end(comm), 2: slice visible(st),
+// 3: after split of the slice(st), 4: after its GEMM(st)}
+inline void rp_mark(b200_rowpanel* rp, int slot, cudaStream_t s) {
+  if (!rp->trace) return;
+  if (!rp->tr[slot]) cudaEventCreate(&rp->tr[slot]);
+  cudaEventRecord(rp->tr[slot], s);
+}
+
 #define RP_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cudaGetLastError(); return (int)e_; } } while (0)
 
 // Enqueues the broadcast of B's K-slices on the comm stream (in place: root sends from, the others
@@ -111,9 +123,11 @@ int rowpanel_broadcast(b200_rowpanel* rp, float* dB, int ldb, int n, int root, c
     if (wait_per_slice && rp->rank == root) RP_CK(cudaStreamWaitEvent(rp->comm_stream, wait_per_slice[j], 0));
     if (rp->world > 1) {
       float* blk = dB + (size_t)rp->k0[j] * ldb;
+      rp_mark(rp, 8 + 6 * j, rp->comm_stream);
       const size_t count = (size_t)(rp->k0[j + 1] - rp->k0[j]) * ldb - (size_t)(ldb - n);
       if (int rc = nccl_check(g_nccl.Broadcast(blk, blk, count, ncclFloat32, root, rp->comm, rp->comm_stream), "ncclBroadcast")) return rc;
     }
+    rp_mark(rp, 8 + 6 * j + 1, rp->comm_stream);
     RP_CK(cudaEventRecord(rp->ev_b[j], rp->comm_stream));
   }
   return 0;
@@ -209,6 +223,24 @@ int b200_rowpanel_create(b200_rowpanel** out, void* nccl_comm, int m_local_max, 
 }
 
 void b200_rowpanel_destroy(b200_rowpanel* rp) { rowpanel_free(rp); }
+// Diagnostics: enable, run one call, then dump: out[0] = A split done, then per slice {bcast begin, bcast end, slice
+// visible on the compute stream, split done, GEMM done}, all in ms after the call's first stream operation.
+void b200_rowpanel_trace(b200_rowpanel* rp, int enable) { if (rp) rp->trace = enable; }
+int b200_rowpanel_trace_dump(b200_rowpanel* rp, float* out, int cap) {
+  if (!rp || !rp->trace || !rp->tr[0]) return 0;
+  cudaDeviceSynchronize();
+  int n = 0;
+  auto get = [&](int slot) { float ms = -1.f; if (rp->tr[slot]) cudaEventElapsedTime(&ms, rp->tr[0], rp->tr[slot]); cudaGetLastError(); return ms; };
+  if (n < cap) out[n++] = get(1);
+  for (int j = 0; j < rp->nslices; j++)
+    for (int e = 0; e < 5; e++) if (n < cap) out[n++] = get(8 + 6 * j + e);
+  return n;
+}
+int b200_rowpanel_set_reserve_sms(b200_rowpanel* rp, int sms) {
+  if (!rp || sms < 0 || sms > 64) return B200_ERR_BAD_ARG;
+  rp->reserve_sms = sms;
+  return 0;
+}
 int b200_rowpanel_slices(const b200_rowpanel* rp, int* bounds, int cap) {
   if (!rp) return 0;
   for (int j = 0; j <= rp->nslices && j < cap; j++) bounds[j] = rp->k0[j];
@@ -228,6 +260,7 @@ int b200_gemm_f32_rowpanel(b200_rowpanel* rp, int m_local, int n, int k, const f
   cudaStream_t st = (cudaStream_t)stream;
   // the exchange: comm stream starts once everything already queued on `st` (producer of B on the root,
   // earlier readers of the receive buffer elsewhere) is done
+  rp_mark(rp, 0, st);
   RP_CK(cudaEventRecord(rp->ev_start, st));
   RP_CK(cudaStreamWaitEvent(rp->comm_stream, rp->ev_start, 0));
   if ((rc = rowpanel_broadcast(rp, dB, ldb, n, root, nullptr))) return rc;
@@ -239,22 +272,32 @@ int b200_gemm_f32_rowpanel(b200_rowpanel* rp, int m_local, int n, int k, const f
     // A_i -> fp16 planes while slice 0 of B travels
     if ((rc = launch_f16_split_rows(dA, lda, m_local, k, rp->a_max, rp->a_planes, rp->a_pitch, m_local, st))) return rc;
     RP_CK(cudaMemsetAsync(rp->b_max, 0, (size_t)rp->nslices * n * 4, st));
+    rp_mark(rp, 1, st);
     for (int j = 0; j < rp->nslices; j++) {
       const int kk0 = rp->k0[j], kr = rp->k0[j + 1] - kk0;
       RP_CK(cudaStreamWaitEvent(st, rp->ev_b[j], 0));
+      rp_mark(rp, 8 + 6 * j + 2, st);
       float* cmax = rp->b_max + (size_t)j * n;
       if ((rc = launch_f16_split_cols(dB + (size_t)kk0 * ldb, ldb, kr, n, cmax, rp->b_planes[j], rp->b_pitch,
                                       rp->b_rows[j], nullptr, 0, st))) return rc;
+      rp_mark(rp, 8 + 6 * j + 3, st);
       const F16Operand oa{rp->a_planes + kk0, rp->a_pitch, m_local, rp->a_max};
       const F16Operand ob{rp->b_planes[j], rp->b_pitch, rp->b_rows[j], cmax};
-      if ((rc = gemm_f16x2_core(m_local, n, kr, oa, ob, dC, ldc, j > 0 ? 1 : 0, st))) return rc;
+      t_sm_reserve = (rp->world > 1 && j + 1 < rp->nslices) ? rp->reserve_sms : 0;
+      rc = gemm_f16x2_core(m_local, n, kr, oa, ob, dC, ldc, j > 0 ? 1 : 0, st);
+      t_sm_reserve = 0;
+      if (rc) return rc;
+      rp_mark(rp, 8 + 6 * j + 4, st);
     }
     return 0;
   }
   for (int j = 0; j < rp->nslices; j++) {
     const int kk0 = rp->k0[j], kr = rp->k0[j + 1] - kk0;
     RP_CK(cudaStreamWaitEvent(st, rp->ev_b[j], 0));
-    if ((rc = gemm_f32_impl(m_local, n, kr, dA + kk0, lda, dB + (size_t)kk0 * ldb, ldb, dC, ldc, rp->mode, j > 0 ? 1 : 0, st))) return rc;
+    t_sm_reserve = (rp->world > 1 && j + 1 < rp->nslices) ? rp->reserve_sms : 0;
+    rc = gemm_f32_impl(m_local, n, kr, dA + kk0, lda, dB + (size_t)kk0 * ldb, ldb, dC, ldc, rp->mode, j > 0 ? 1 : 0, st);
+    t_sm_reserve = 0;
+    if (rc) return rc;
   }
   return 0;
 }

@@ -77,6 +77,9 @@ class RowPanelPlan:
             rows = [k1 - k0 for k0, k1 in slices]
             arr, cnt = (C.c_int * len(rows))(*rows), len(rows)
         pkg._check(self.lib.b200_rowpanel_create(C.byref(self.handle), C.c_void_p(comm_ptr), m_local_max, n, k, mode, arr, cnt))
+        import os
+        if os.environ.get("B200_RESERVE_SMS"):      # tuning: SMs left to the exchange while a later slice is in flight
+            pkg._check(self.lib.b200_rowpanel_set_reserve_sms(self.handle, int(os.environ["B200_RESERVE_SMS"])))
         b = (C.c_int * 17)()
         ns = self.lib.b200_rowpanel_slices(self.handle, b, 17)
         self.chunks = [(b[j], b[j + 1]) for j in range(ns)]

@@ -222,6 +222,14 @@ int  b200_comm_destroy(void* nccl_comm);
 int  b200_rowpanel_create(b200_rowpanel** out, void* nccl_comm, int m_local_max, int n, int k,
                           int precision_mode, const int* slice_rows, int n_slices);
 void b200_rowpanel_destroy(b200_rowpanel* plan);
+/* SMs the GEMMs of all but the last K-slice leave free for the exchange (default 16): a persistent GEMM that holds
+ * every SM starves NCCL's copy kernels, and the slices then arrive only between GEMMs. */
+int  b200_rowpanel_set_reserve_sms(b200_rowpanel* plan, int sms);
+/* Diagnostics: with tracing on, timing events bracket every stage of a call; the dump synchronises the device and
+ * writes, in ms after the call began: A split done, then per K-slice {broadcast begin, broadcast end, slice visible
+ * on the compute stream, split done, GEMM done}.  Returns the number of values. */
+void b200_rowpanel_trace(b200_rowpanel* plan, int enable);
+int  b200_rowpanel_trace_dump(b200_rowpanel* plan, float* out_ms, int cap);
 /* K-slice boundaries of the plan: writes min(n_slices + 1, cap) row offsets, returns n_slices. */
 int  b200_rowpanel_slices(const b200_rowpanel* plan, int* bounds, int cap);
 /* C_local = A_local * B on DEVICE pointers (dB: the operand on root, the receive buffer elsewhere; ldb == n
@@ -263,6 +271,10 @@ int b200_convert_f32_to_bf16(const float* dSrc, uint16_t* dDst, size_t count,
  * MN-major B operand (bytes; 0 = library default).  Used only by the probe in
  * tests/ to pin the descriptor semantics on real hardware. */
 void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes);
+/* Tuning hook: 0 = launch without programmatic dependent launch (default 1: the library's tensor-core and
+ * pre-pass kernels are launched with the programmatic-serialisation attribute and order themselves with
+ * griddepcontrol.wait, so a kernel's prologue overlaps the tail of its predecessor in the stream). */
+void b200_gemm_debug_set_pdl(int on);
 /* Tuning hook: force the tensor-core tile width (128, 192 or 256; 0 = built-in heuristic). */
 void b200_gemm_debug_set_bn(int bn);
 /* Tuning hook: 1 = single-CTA tiles only, 2 = CTA pairs (tcgen05 cta_group::2) always, 0 = auto. */

@@ -81,3 +81,36 @@ g.lib.b200_gemm_debug_set_split_chunk(512, 512)
 out["f16x2_sweep"] = sweep
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"probe_r2_{N}.json"), "w"), indent=1)
+
+# ---- programmatic dependent launch on / off, and the 4-bit path ------------------------------------------
+pdl = {}
+bf = [((torch.rand(N, N, device=dev) - 0.5).bfloat16(), (torch.rand(N, N, device=dev) - 0.5).bfloat16()) for _ in range(R)]
+i8 = [(torch.randint(-127, 128, (N, N), device=dev, dtype=torch.int8), torch.randint(-127, 128, (N, N), device=dev, dtype=torch.int8)) for _ in range(R)]
+ob = [torch.empty(N, N, device=dev, dtype=torch.bfloat16) for _ in range(R)]
+oi = [torch.empty(N, N, device=dev, dtype=torch.int32) for _ in range(R)]
+for on in (1, 0, 1):
+    g.lib.b200_gemm_debug_set_pdl(on)
+    pdl[f"f16x2_step_ms_pdl{on}"] = timeit(lambda i: g.gemm_f32(sets[i % R][0], sets[i % R][1], out=sets[i % R][2], mode=5))
+    pdl[f"bf16x3_step_ms_pdl{on}"] = timeit(lambda i: g.gemm_f32(sets[i % R][0], sets[i % R][1], out=sets[i % R][2], mode=2))
+    pdl[f"bf16_obf16_ms_pdl{on}"] = timeit(lambda i: g.gemm_bf16(bf[i % R][0], bf[i % R][1], out=ob[i % R]))
+    pdl[f"s8_ms_pdl{on}"] = timeit(lambda i: g.gemm_s8s32(i8[i % R][0], i8[i % R][1], out=oi[i % R]))
+    print({k: round(v, 5) for k, v in pdl.items() if k.endswith(str(on))}, flush=True)
+out["pdl"] = pdl
+g.gemm_f32(sets[0][0], sets[0][1], out=sets[0][2], mode=5)
+out["f16x2_rel_err_after_pdl"] = err(sets[0][2])
+del bf, i8, ob, oi
+mx = {}
+for n in (4096, 8192):
+    A = torch.rand(n, n, device=dev) * 2 - 1
+    B = torch.rand(n, n, device=dev) * 2 - 1
+    t_qa = timeit(lambda i: g.mxf4_quantize(A), iters=5)
+    t_qb = timeit(lambda i: g.mxf4_quantize(B, transpose=True), iters=5)
+    qa, sfa, _, _ = g.mxf4_quantize(A)
+    qb, sfb, _, _ = g.mxf4_quantize(B, transpose=True)
+    Cm = torch.empty(n, n, device=dev)
+    t = timeit(lambda i: g.gemm_mxf4(qa, sfa, qb, sfb, n, n, n, out=Cm))
+    mx[n] = {"gemm_ms": t, "tflops": 2.0 * n ** 3 / t / 1e9, "quantize_a_ms_incl_malloc": t_qa, "quantize_b_t_ms_incl_malloc": t_qb}
+    print("mxf4", n, mx[n], flush=True)
+    del A, B, qa, qb, sfa, sfb, Cm
+out["mxf4"] = mx
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"probe_r2_{N}.json"), "w"), indent=1)
