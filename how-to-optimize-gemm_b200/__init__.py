@@ -31,7 +31,7 @@ EXPORTS = [
     "b200_convert_f32_to_bf16", "b200_gemm_debug_set_b_desc", "b200_gemm_debug_set_bn",
     "b200_gemm_debug_set_split_chunk", "b200_gemm_debug_kernel_timing", "b200_gemm_debug_kernel_time_ms",
     "b200_gemm_debug_set_cta_group", "b200_gemm_debug_set_split_tail", "b200_gemm_debug_set_group_rows",
-    "b200_gemm_debug_set_ffma_variant", "b200_gemm_debug_set_epilogue", "b200_gemm_debug_set_pdl",
+    "b200_gemm_debug_set_ffma_variant", "b200_gemm_debug_set_epilogue", "b200_gemm_debug_set_pdl", "b200_gemm_debug_set_dynamic_sched",
 ]
 
 
@@ -103,6 +103,7 @@ lib.b200_gemm_debug_kernel_timing.argtypes = [_i]
 lib.b200_gemm_debug_set_cta_group.argtypes = [_i]
 lib.b200_gemm_debug_set_split_tail.argtypes = [_i]
 lib.b200_gemm_debug_set_pdl.argtypes = [_i]
+lib.b200_gemm_debug_set_dynamic_sched.argtypes = [_i]
 lib.b200_gemm_debug_kernel_time_ms.argtypes = [C.POINTER(C.c_double)]
 
 
@@ -159,7 +160,9 @@ def MY_MMult_int8(m, n, k, a, lda, b, ldb, c, ldc):
 
 # ---- tensor forms (torch CUDA tensors; row-major, last dim contiguous) --------------------------
 def _ld(t):
-    assert t.dim() == 2 and t.stride(1) == 1, "row-major 2-D tensor with unit inner stride expected"
+    assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] <= 1), "row-major 2-D tensor with unit inner stride expected"
+    if t.shape[1] <= 1:              # a single column: any stride is reported for the size-1 dimension
+        return max(1, t.stride(0)) if t.shape[0] > 1 else 1
     return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
 
 

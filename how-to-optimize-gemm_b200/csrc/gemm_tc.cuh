@@ -78,6 +78,10 @@ struct TcParams {
   int full_tiles, split;
   int halfn;               // 1: tail tiles are issued as two half-width (BN/2) tiles instead of K parts
   int* flags;              // [tail tile][cta rank][epilogue warp], zero between launches
+  // Dynamic tile scheduler: work items are handed out in order by an atomic counter (zero between launches; the
+  // unit that draws the last sentinel resets it), so a CTA that starts late — SMs held by a co-running kernel such
+  // as NCCL's copy kernels — simply draws fewer tiles instead of delaying the whole grid.  Null = static round robin.
+  int* sched_counter;
   // Scaled split mode (B200_F32_F16X2): operands were multiplied by 2^-e(row) / 2^-e(col) before the
   // fp16 split; the epilogue multiplies back by 2^e(row) * 2^e(col), exact.  Null = no scaling.
   const float* row_max;    // [M] max |A(i,:)|
@@ -121,10 +125,12 @@ struct TcConfig {
   static constexpr int EPI_STAGING = EPI_WARPS * 32 * 128;  // per epilogue warp: 32 rows x 128 B
   static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;  // TMEM columns between the two accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int SCHED_SLOTS = 8;                     // ring of published work items (never the limiter: draws are gated by the producer, see run_tile_scheduler)
+  static constexpr int SCHED_WARP = REGACC ? 2 : EPI_WARP0 + EPI_WARPS;   // REGACC: an otherwise idle warp of the data-movement warpgroup
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * SCHED_SLOTS + 1;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_STAGING +
-                                    NUM_BARS * 8 + 16;
-  static constexpr int THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
+                                    NUM_BARS * 8 + 16 + 4 * SCHED_SLOTS;
+  static constexpr int THREADS = 32 * (EPI_WARP0 + EPI_WARPS + (REGACC ? 0 : 1));   // + the scheduler warp
   static_assert(!REGACC || BN % 64 == 0, "register accumulation splits the tile columns over two warp sets of 32-column groups");
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
   static_assert(BN_CTA % B_BOX_COLS == 0 && BN % 16 == 0 && BN <= 256, "invalid BN");
@@ -182,6 +188,36 @@ __device__ __forceinline__ WorkItem work_item(int w, const TcParams& p, int num_
   return it;
 }
 
+// Per-warp view of the tile schedule.  Static: item = unit, unit + num_units, ...  Dynamic: items arrive through a
+// ring of SCHED_SLOTS shared-memory slots written (in both CTAs of a pair) by the scheduler warp of the leader CTA;
+// every consumer warp reads each slot once and releases it on the LEADER's empty barrier.  -1 ends the loop.
+struct TileSched {
+  int slot;
+  uint32_t phase;
+  int w;                           // static mode: the next item of this unit
+  // bar_sfull: own CTA's full[] (shared::cta); sempty_leader: the leader's empty[] (shared::cluster when pair)
+  // gate != 0 (the leader's producer warp only): barrier to arrive on after taking an item — the scheduler draws the
+  // next item only then, so a unit never claims work more than one item ahead of its producer
+  __device__ __forceinline__ int next(int lane, bool dynamic, bool pair, uint32_t bar_sfull, uint32_t sempty_leader,
+                                      const volatile int* items, int step, int num_items, uint32_t gate = 0) {
+    if (!dynamic) {
+      const int r = w;
+      w += step;
+      return r < num_items ? r : -1;
+    }
+    mbar_wait_cluster(bar_sfull + 8 * slot, phase);
+    const int r = items[slot];
+    __syncwarp();
+    if (lane == 0) {
+      if (pair) mbar_arrive_cluster(sempty_leader + 8 * slot);
+      else mbar_arrive(sempty_leader + 8 * slot);
+      if (gate) mbar_arrive(gate);
+    }
+    if (++slot == 8) { slot = 0; phase ^= 1; }
+    return r;
+  }
+};
+
 template <typename OutT> struct OutPack;
 template <> struct OutPack<float> {
   static constexpr int COLS = 32;   // accumulator columns per 128-byte staging row
@@ -222,6 +258,37 @@ template <typename OutT> struct OutBytes { static constexpr int V = 4; };
 template <> struct OutBytes<bf16_out> { static constexpr int V = 2; };
 template <> struct OutBytes<s8_out> { static constexpr int V = 1; };
 
+// The scheduler warp of the leader CTA: draws work items from the global counter and publishes each one in a slot of
+// BOTH CTAs of the pair (remote shared-memory store + remote barrier arrive); -1 after the last item.
+template <int CG, int SLOTS>
+__device__ __forceinline__ void run_tile_scheduler(const TcParams& p, int lane, int num_items, int num_units,
+                                                   uint32_t bar_sfull, uint32_t bar_sempty, uint32_t s_items, uint32_t bar_gate) {
+  int slot = 0;
+  uint32_t ph = 0, gph = 0;
+  const int total = num_items + num_units;              // every unit draws exactly one sentinel
+  for (int i = 0;; i++) {
+    if (i > 0) {                                        // draw item i only once the producer has taken item i - 1:
+      mbar_wait(bar_gate, gph);                         // work is claimed late, so late or slow units claim less
+      gph ^= 1;
+    }
+    mbar_wait_cluster(bar_sempty + 8 * slot, ph ^ 1);
+    int w = 0;
+    if (lane == 0) {
+      w = atomicAdd(p.sched_counter, 1);
+      if (w == total - 1) atomicExch(p.sched_counter, 0);              // last draw of the launch: re-arm for a later one
+      const uint32_t item = (uint32_t)(w < num_items ? w : -1);
+#pragma unroll
+      for (int r = 0; r < CG; r++) {
+        st_shared_cluster_u32(mapa(s_items + 4 * slot, r), item);
+        mbar_arrive_cluster(mapa(bar_sfull + 8 * slot, r));            // release.cluster: orders the store above
+      }
+    }
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w >= num_items) break;
+    if (++slot == SLOTS) { slot = 0; ph ^= 1; }
+  }
+}
+
 template <int KIND, int BN, int STAGES, typename OutT, class Prod, int A_ROW_BYTES, int CG, int EPIW>
 __global__ void __launch_bounds__((TcConfig<KIND, BN, STAGES, Prod, A_ROW_BYTES, CG, EPIW>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -241,6 +308,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t bar_tfull = sBar + 16 * STAGES;
   const uint32_t bar_tempty = bar_tfull + 16;
   const uint32_t s_tmem_ptr = bar_tempty + 16;
+  const uint32_t bar_sfull = s_tmem_ptr + 16;
+  const uint32_t bar_sempty = bar_sfull + 8 * Cfg::SCHED_SLOTS;
+  const uint32_t bar_gate = bar_sempty + 8 * Cfg::SCHED_SLOTS;
+  const uint32_t s_items = bar_gate + 8;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5;
@@ -263,6 +334,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(bar_tfull + 8 * i, 1);
       mbar_init(bar_tempty + 8 * i, Cfg::EPI_WARPS * CG);     // one arrive per epilogue warp of every CTA in the pair
     }
+    for (int i = 0; i < Cfg::SCHED_SLOTS; i++) {
+      mbar_init(bar_sfull + 8 * i, 1);                                  // the scheduler warp's arrive
+      mbar_init(bar_sempty + 8 * i, CG * (1 + Cfg::EPI_WARPS) + 1);     // producer + epilogue warps of every CTA, + the MMA warp
+    }
+    mbar_init(bar_gate, 1);                                             // the leader's producer warp: "took an item"
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -281,6 +357,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int num_items = p.full_tiles + (num_tiles - p.full_tiles) * (p.halfn ? 2 : p.split);
   const int num_kb = (p.K + Cfg::BK - 1) / Cfg::BK;
+  TileSched sched;
+  sched.slot = 0; sched.phase = 0; sched.w = unit;
+  const bool dyn = p.sched_counter != nullptr;
+#define NEXT_ITEM_G(GATE) sched.next(lane, dyn, CG == 2, bar_sfull, CG == 2 ? mapa(bar_sempty, 0) : bar_sempty, \
+                                     reinterpret_cast<const volatile int*>(smem_gen + (s_items - smem_base)), num_units, num_items, GATE)
+#define NEXT_ITEM() NEXT_ITEM_G(0u)
 
   if (warp < Cfg::EPI_WARP0) {
   // register pool of the CTA = 384 threads x 168 (launch bound); afterwards 128 x 88 + 256 x 208 = the same 64512
@@ -292,7 +374,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     {
       int s = 0;
       uint32_t ph = 0;
-      for (int w = unit; w < num_items; w += num_units) {
+      const uint32_t gate = leader ? bar_gate : 0u;
+      for (int w = NEXT_ITEM_G(gate); w >= 0; w = NEXT_ITEM_G(gate)) {
         const WorkItem it = work_item<BN>(w, p, num_kb);
         int mb, nb;
         tile_coords(it.tile, p.tiles_m, p.tiles_n, p.group_m, mb, nb);
@@ -341,7 +424,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int w = unit; w < num_items; w += num_units) {
+      for (int w = NEXT_ITEM(); w >= 0; w = NEXT_ITEM()) {
        const WorkItem it = work_item<BN>(w, p, num_kb);
        const uint32_t idesc = make_idesc(T::C_FMT, T::AB_FMT, /*a_mn=*/0, /*b_mn=*/1, Cfg::TILE_M, it.bn);
        for (int c0 = it.kb0; c0 < it.kb1; c0 += p.chunk_kb) {     // one TMEM accumulator per K-chunk
@@ -382,7 +465,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
        }
       }
     }
+  } else if (Cfg::REGACC && warp == Cfg::SCHED_WARP) {
+    if (dyn && leader)
+      run_tile_scheduler<CG, Cfg::SCHED_SLOTS>(p, lane, num_items, num_units, bar_sfull, bar_sempty, s_items, bar_gate);
   }
+  } else if (!Cfg::REGACC && warp == Cfg::SCHED_WARP) {
+    if (dyn && leader)
+      run_tile_scheduler<CG, Cfg::SCHED_SLOTS>(p, lane, num_items, num_units, bar_sfull, bar_sempty, s_items, bar_gate);
   } else {
    if constexpr (Cfg::REGACC) {
     setmaxnreg_inc<208>();
@@ -401,7 +490,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0;
     uint32_t aph = 0;
     const uint32_t tempty_base = CG == 2 ? mapa(bar_tempty, 0) : bar_tempty;   // leader's barrier
-    for (int w = unit; w < num_items; w += num_units) {
+    for (int w = NEXT_ITEM(); w >= 0; w = NEXT_ITEM()) {
       const WorkItem it = work_item<BN>(w, p, num_kb);
       int mb, nb;
       tile_coords(it.tile, p.tiles_m, p.tiles_n, p.group_m, mb, nb);
@@ -529,7 +618,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0;
     uint32_t aph = 0;
     const uint32_t tempty_base = CG == 2 ? mapa(bar_tempty, 0) : bar_tempty;   // leader's barrier
-    for (int w = unit; w < num_items; w += num_units) {
+    for (int w = NEXT_ITEM(); w >= 0; w = NEXT_ITEM()) {
       const WorkItem it = work_item<BN>(w, p, num_kb);
       int mb, nb;
       tile_coords(it.tile, p.tiles_m, p.tiles_n, p.group_m, mb, nb);
@@ -753,6 +842,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   }
 
+#undef NEXT_ITEM
+#undef NEXT_ITEM_G
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync(); else __syncthreads();   // no CTA may exit while its peer still signals it
   if (warp == 1) {

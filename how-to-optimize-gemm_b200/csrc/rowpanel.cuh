@@ -67,7 +67,8 @@ struct b200_rowpanel {
   int nslices = 0;
   int trace = 0;            // diagnostics: timing events around every stage of the last call (b200_rowpanel_trace)
   cudaEvent_t tr[8 + 6 * kMaxSlices] = {};
-  int reserve_sms = 16;     // SMs the GEMMs of all but the last K-slice leave to the exchange's copy kernels
+  int reserve_sms = 0;      // SMs the GEMMs of all but the last K-slice leave to the exchange's copy kernels
+  int dynamic_sched = 1;    // those GEMMs draw their tiles dynamically (they share the GPU with NCCL's copy kernels)
   int k0[kMaxSlices + 1] = {};
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_b[kMaxSlices] = {}, ev_done = nullptr;
@@ -237,7 +238,8 @@ int b200_rowpanel_trace_dump(b200_rowpanel* rp, float* out, int cap) {
   return n;
 }
 int b200_rowpanel_set_reserve_sms(b200_rowpanel* rp, int sms) {
-  if (!rp || sms < 0 || sms > 64) return B200_ERR_BAD_ARG;
+  if (!rp || sms < -1 || sms > 64) return B200_ERR_BAD_ARG;
+  if (sms == -1) { rp->dynamic_sched = 0; return 0; }       // tuning: static schedule for the co-running GEMMs too
   rp->reserve_sms = sms;
   return 0;
 }
@@ -283,9 +285,11 @@ int b200_gemm_f32_rowpanel(b200_rowpanel* rp, int m_local, int n, int k, const f
       rp_mark(rp, 8 + 6 * j + 3, st);
       const F16Operand oa{rp->a_planes + kk0, rp->a_pitch, m_local, rp->a_max};
       const F16Operand ob{rp->b_planes[j], rp->b_pitch, rp->b_rows[j], cmax};
-      t_sm_reserve = (rp->world > 1 && j + 1 < rp->nslices) ? rp->reserve_sms : 0;
+      const bool corun = rp->world > 1 && j + 1 < rp->nslices;      // a later slice is still being broadcast
+      t_sm_reserve = corun ? rp->reserve_sms : 0;
+      t_dynamic_sched = corun ? rp->dynamic_sched : 0;
       rc = gemm_f16x2_core(m_local, n, kr, oa, ob, dC, ldc, j > 0 ? 1 : 0, st);
-      t_sm_reserve = 0;
+      t_sm_reserve = 0; t_dynamic_sched = 0;
       if (rc) return rc;
       rp_mark(rp, 8 + 6 * j + 4, st);
     }
@@ -294,9 +298,11 @@ int b200_gemm_f32_rowpanel(b200_rowpanel* rp, int m_local, int n, int k, const f
   for (int j = 0; j < rp->nslices; j++) {
     const int kk0 = rp->k0[j], kr = rp->k0[j + 1] - kk0;
     RP_CK(cudaStreamWaitEvent(st, rp->ev_b[j], 0));
-    t_sm_reserve = (rp->world > 1 && j + 1 < rp->nslices) ? rp->reserve_sms : 0;
+    const bool corun = rp->world > 1 && j + 1 < rp->nslices;
+    t_sm_reserve = corun ? rp->reserve_sms : 0;
+    t_dynamic_sched = corun ? rp->dynamic_sched : 0;
     rc = gemm_f32_impl(m_local, n, kr, dA + kk0, lda, dB + (size_t)kk0 * ldb, ldb, dC, ldc, rp->mode, j > 0 ? 1 : 0, st);
-    t_sm_reserve = 0;
+    t_sm_reserve = 0; t_dynamic_sched = 0;
     if (rc) return rc;
   }
   return 0;

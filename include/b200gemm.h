@@ -222,8 +222,9 @@ int  b200_comm_destroy(void* nccl_comm);
 int  b200_rowpanel_create(b200_rowpanel** out, void* nccl_comm, int m_local_max, int n, int k,
                           int precision_mode, const int* slice_rows, int n_slices);
 void b200_rowpanel_destroy(b200_rowpanel* plan);
-/* SMs the GEMMs of all but the last K-slice leave free for the exchange (default 16): a persistent GEMM that holds
- * every SM starves NCCL's copy kernels, and the slices then arrive only between GEMMs. */
+/* Tuning.  While a later K-slice is still being broadcast, the GEMM of the current slice shares the GPU with NCCL's
+ * copy kernels; those GEMMs therefore draw their tiles from an atomic counter (dynamic schedule: a CTA that gets its
+ * SM late draws fewer tiles) and may leave `sms` SMs unused (default 0).  sms = -1 switches the dynamic schedule off. */
 int  b200_rowpanel_set_reserve_sms(b200_rowpanel* plan, int sms);
 /* Diagnostics: with tracing on, timing events bracket every stage of a call; the dump synchronises the device and
  * writes, in ms after the call began: A split done, then per K-slice {broadcast begin, broadcast end, slice visible
@@ -275,6 +276,9 @@ void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes);
  * pre-pass kernels are launched with the programmatic-serialisation attribute and order themselves with
  * griddepcontrol.wait, so a kernel's prologue overlaps the tail of its predecessor in the stream). */
 void b200_gemm_debug_set_pdl(int on);
+/* Tuning hook: 0 = static round-robin tile schedule (default 1: a scheduler warp hands tiles out from an atomic
+ * counter, so CTAs that start late because a co-running kernel holds their SM draw fewer tiles). */
+void b200_gemm_debug_set_dynamic_sched(int on);
 /* Tuning hook: force the tensor-core tile width (128, 192 or 256; 0 = built-in heuristic). */
 void b200_gemm_debug_set_bn(int bn);
 /* Tuning hook: 1 = single-CTA tiles only, 2 = CTA pairs (tcgen05 cta_group::2) always, 0 = auto. */
