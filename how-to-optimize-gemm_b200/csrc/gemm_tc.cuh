@@ -500,6 +500,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = nb * BN + it.nsub * it.bn + half * hc;
       const uint32_t t_col = (uint32_t)(half * hc);
       float acc[NJ][32];
+      const int my_re = (p.row_max != nullptr && m0 + lane < p.M) ? pow2_exp(__ldg(p.row_max + m0 + lane)) : 0;
       bool first = true;
       for (int c0 = it.kb0; c0 < it.kb1; c0 += p.chunk_kb) {
         mbar_wait(bar_tfull + 8 * as, aph);
@@ -548,11 +549,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float al = p.axpby ? p.alpha : 1.f;
       const float be = (p.axpby && it.part == 0) ? p.beta : 1.f;
       const int chunk = lane & 7;
+      // (ncu, round 2: the first version fetched the row maximum inside the store loop — 32 dependent L2 round trips per
+      //  tile — and unrolled that loop 32 times into 150 KB of code: stall_long_sb + stall_no_inst, 13-19 us per tile.)
+      // my_re: scale exponent of the row this lane OWNS (row = lane), one coalesced load per tile issued before the
+      // accumulation loop's results are needed; the store loop gets row exponents by shuffle.
 #pragma unroll
       for (int j = 0; j < NJ; j++) {
         if (j < nj) {
           const int col = n0 + j * 32 + chunk * 4;
           const bool vec = p.vec_ok && col + 4 <= p.N;
+          int ce[4] = {0, 0, 0, 0};
+          if (p.col_max != nullptr) {                 // issued before the staging round trip: latency overlaps it
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+              if (col + e < p.N) ce[e] = pow2_exp(__ldg(p.col_max + col + e));
+          }
+          if (fold && vec) {                          // C tile lines of this group towards L1 while the transpose runs
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const int gm = m0 + i * 4 + (lane >> 3);
+              if (gm < p.M) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const float*>(p.C) + (long long)gm * p.ldc + col));
+            }
+          }
           // registers (row = lane) -> staging, 16-byte chunk index XOR (row & 7): conflict-free both ways
 #pragma unroll
           for (int g = 0; g < 8; g++) {
@@ -561,20 +579,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             *reinterpret_cast<uint4*>(stg + lane * 128 + ((g ^ (lane & 7)) << 4)) = v;
           }
           __syncwarp();
-          int ce[4] = {0, 0, 0, 0};
-          if (p.col_max != nullptr) {
-#pragma unroll
-            for (int e = 0; e < 4; e++)
-              if (col + e < p.N) ce[e] = pow2_exp(__ldg(p.col_max + col + e));
-          }
-#pragma unroll
+#pragma unroll 1
           for (int i = 0; i < 8; i++) {
             const int row = i * 4 + (lane >> 3);
             const int gm = m0 + row;
+            const int re = __shfl_sync(0xffffffffu, my_re, row);
             float4 v = *reinterpret_cast<const float4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4));
             if (gm < p.M) {
               if (p.row_max != nullptr) {                // undo the operand scaling: exact powers of two
-                const int re = pow2_exp(__ldg(p.row_max + gm));
                 v.x = mul_pow2(v.x, re + ce[0]); v.y = mul_pow2(v.y, re + ce[1]);
                 v.z = mul_pow2(v.z, re + ce[2]); v.w = mul_pow2(v.w, re + ce[3]);
               }
@@ -582,7 +594,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (p.axpby) { v.x *= al; v.y *= al; v.z *= al; v.w *= al; }
               if (vec) {
                 if (fold) {                              // once per tile: C += A*B, beta * C, or an earlier K part
-                  const float4 o = __ldcg(reinterpret_cast<const float4*>(dst));
+                  // parts of a K-split tile were written by another SM in this launch: read them at L2, not through L1
+                  const float4 o = it.part > 0 ? __ldcg(reinterpret_cast<const float4*>(dst)) : *reinterpret_cast<const float4*>(dst);
                   if (p.axpby) { v.x = fmaf(be, o.x, v.x); v.y = fmaf(be, o.y, v.y); v.z = fmaf(be, o.z, v.z); v.w = fmaf(be, o.w, v.w); }
                   else { v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
                 }
@@ -756,28 +769,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
         // staging -> global: 8 lanes cover one 128-byte row segment, 4 rows per instruction
-        int ce[4] = {0, 0, 0, 0};
-        if constexpr (std::is_same<OutT, float>::value) {
-          if (p.col_max != nullptr) {
-#pragma unroll
-            for (int e = 0; e < 4; e++)
-              if (col + e < p.N) ce[e] = pow2_exp(__ldg(p.col_max + col + e));
-          }
-        }
+        // (operand scalings exist only in the split modes, whose tiles take the register-accumulation epilogue above)
 #pragma unroll
         for (int i = 0; i < 8; i++) {
           const int row = i * 4 + (lane >> 3);
           const int gm = m0 + row;
           uint4 v = *reinterpret_cast<const uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4));
-          if constexpr (std::is_same<OutT, float>::value) {
-            if (p.row_max != nullptr && gm < p.M) {      // undo the operand scaling: exact powers of two
-              const int re = pow2_exp(__ldg(p.row_max + gm));
-              v.x = __float_as_uint(mul_pow2(__uint_as_float(v.x), re + ce[0]));
-              v.y = __float_as_uint(mul_pow2(__uint_as_float(v.y), re + ce[1]));
-              v.z = __float_as_uint(mul_pow2(__uint_as_float(v.z), re + ce[2]));
-              v.w = __float_as_uint(mul_pow2(__uint_as_float(v.w), re + ce[3]));
-            }
-          }
           if (gm < p.M) {
             uint8_t* dst = reinterpret_cast<uint8_t*>(p.C) + ((long long)gm * p.ldc + col) * OB;
             if (vec) {

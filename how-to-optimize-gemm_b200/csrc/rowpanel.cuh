@@ -180,8 +180,7 @@ int b200_rowpanel_create(b200_rowpanel** out, void* nccl_comm, int m_local_max, 
   rp->m_max = m_local_max; rp->n = n; rp->k = k;
   rp->mode = resolve_f32_mode(precision_mode);
   // K-slices: the caller's row counts (must add up to k, boundaries multiples of 8), else by default
-  // one slice on a single rank and (1, 3, 4)-weighted slices otherwise — a short first slice shortens
-  // the only part of the exchange the math cannot hide behind.
+  // one slice on a single rank and two slices weighted 1 : 3 otherwise.
   if (n_slices > 0 && slice_rows) {
     int acc = 0;
     for (int j = 0; j < n_slices; j++) {
@@ -193,14 +192,13 @@ int b200_rowpanel_create(b200_rowpanel** out, void* nccl_comm, int m_local_max, 
   } else if (rp->world == 1 || k < 1024) {
     rp->nslices = 1; rp->k0[0] = 0; rp->k0[1] = k;
   } else {
-    const int w[3] = {1, 3, 4};
-    int acc = 0, wsum = 0;
-    rp->nslices = 3;
-    for (int j = 0; j < 3; j++) {
-      rp->k0[j] = acc; wsum += w[j];
-      acc = j == 2 ? k : (int)(((long long)k * wsum / 8 + 63) / 64 * 64);
-    }
-    rp->k0[3] = k;
+    // two slices, 1 : 3.  Every extra slice costs a GEMM launch with its own pass over C (~30 us at 4096^2) and every
+    // ncclBroadcast ~40 us of fixed latency, so more slices lose more than a shorter first slice gains (measured on
+    // 2 x B200, profiles/r02_rowpanel_trace.txt: [512,1536,2048] 0.58 ms, [2048,2048] 0.48, [1024,3072] 0.47).
+    rp->nslices = 2;
+    rp->k0[0] = 0;
+    rp->k0[1] = (int)(((long long)k / 4 + 63) / 64 * 64);
+    rp->k0[2] = k;
   }
 #define RP_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cudaGetLastError(); rowpanel_free(rp); return (int)e_; } } while (0)
   RP_TRY(cudaStreamCreateWithFlags(&rp->comm_stream, cudaStreamNonBlocking));

@@ -25,14 +25,13 @@ def row_panel(rank, world, M):
 
 
 def default_slices(K, world):
-    """The C++ plan's default K-slices (b200_rowpanel_create): one slice on a single rank or for a short
-    K, else three slices weighted 1:3:4 with boundaries rounded up to 64 rows — a short first slice
-    shortens the only part of the exchange the math cannot hide behind."""
+    """The C++ plan's default K-slices (b200_rowpanel_create): one slice on a single rank or for a short K, else two
+    slices weighted 1 : 3 with the boundary rounded up to 64 rows — a shorter first slice shortens the only part of the
+    exchange the math cannot hide behind; more slices cost more (a GEMM launch and an NCCL call each) than they gain."""
     if world == 1 or K < 1024:
         return [(0, K)]
-    e1 = (K * 1 // 8 + 63) // 64 * 64
-    e2 = (K * 4 // 8 + 63) // 64 * 64
-    return [(0, e1), (e1, e2), (e2, K)]
+    e1 = (K // 4 + 63) // 64 * 64
+    return [(0, e1), (e1, K)]
 
 
 def row_chunks(K, chunks, align=64):

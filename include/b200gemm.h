@@ -211,7 +211,7 @@ int b200_gemm_s8s8_requant(int m, int n, int k,
  *               made with b200_comm_unique_id + b200_comm_init_rank (rank 0 creates the 128-byte id and
  *               hands it to the other ranks by whatever means the host has).  NULL = single rank.
  *   slice_rows  rows of B per K-slice (sum k, every boundary a multiple of 8), or NULL / n_slices 0 for the
- *               default (one slice on one rank, else three slices weighted 1:3:4).
+ *               default (one slice on one rank, else two slices weighted 1:3).
  * The plan owns all scratch (planes, events, streams): the compute calls never allocate. */
 typedef struct b200_rowpanel b200_rowpanel;
 int  b200_nccl_load(const char* libnccl_path_or_null);

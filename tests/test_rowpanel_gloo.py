@@ -86,10 +86,10 @@ def test_partition_helpers():
     assert rowpanel.row_chunks(200, (1, 3, 4)) == [(0, 128), (128, 200)]        # 25 rows round to no block
     # the C++ plan's default schedule (b200_rowpanel_create), mirrored by default_slices
     assert rowpanel.default_slices(4096, 1) == [(0, 4096)]
-    assert rowpanel.default_slices(4096, 2) == [(0, 512), (512, 2048), (2048, 4096)]
-    assert rowpanel.default_slices(16384, 8) == [(0, 2048), (2048, 8192), (8192, 16384)]
+    assert rowpanel.default_slices(4096, 2) == [(0, 1024), (1024, 4096)]
+    assert rowpanel.default_slices(16384, 8) == [(0, 4096), (4096, 16384)]
     assert rowpanel.default_slices(1000, 4) == [(0, 1000)]
-    assert rowpanel.default_slices(1100, 2) == [(0, 192), (192, 576), (576, 1100)]
+    assert rowpanel.default_slices(1100, 2) == [(0, 320), (320, 1100)]
     for K in (1, 63, 64, 200, 4096, 16384):
         for w in ((1, 3, 4), (1, 1), (5,), (1, 2, 2, 3)):
             ch = rowpanel.row_chunks(K, w)
