@@ -777,10 +777,10 @@ int gemm_f32_impl(int m, int n, int k, const float* dA, int lda, const float* dB
   // TFLOP/s at 512^3, 2.0 vs 2.0 at 256^3) and bit-exact against the reference oracle.  From 640^3 the
   // tensor-core path pulls away (19.2 vs 15.0; 63.0 vs 41.0 at 1024^3).
   if (was_auto && (mode == B200_F32_BF16X3 || mode == B200_F32_F16X2) && tma && (double)m * n * k <= 2.0e8) mode = B200_F32_STRICT;
-  // AUTO between ~640^3 and ~1440^3: the two-launch BF16X3 path (one fused split + GEMM) beats the four-launch
-  // F16X2 path while launches, not tensor work, dominate (measured in bench.py's sweep: 1024^3 63 vs 48 TFLOP/s,
-  // 1536^3 159 vs 154, 1792^3 175 vs 205).  Both are fp32-class.
-  else if (was_auto && mode == B200_F32_F16X2 && (double)m * n * k < 3.0e9) mode = B200_F32_BF16X3;
+  // AUTO between ~640^3 and ~1100^3: the two-launch BF16X3 path (one fused split + GEMM) beats the four-launch
+  // F16X2 path while launches, not tensor work, dominate (tools/probe_crossover.py, TFLOP/s BF16X3 : F16X2 —
+  // 768^3 23.6 : 20.1, 1024^3 61.5 : 53.4, 1152^3 98.5 : 98.7, 1536^3 170 : 193, 2048^3 201 : 252).  Both are fp32-class.
+  else if (was_auto && mode == B200_F32_F16X2 && (double)m * n * k < 1.3e9) mode = B200_F32_BF16X3;
   switch (mode) {
     case B200_F32_STRICT:
       // 128x256 fat-thread tiles once they fill most of the machine (measured at N = 4096 / 3072 / 2048:

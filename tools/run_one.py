@@ -1,5 +1,5 @@
 """Launch one kernel family a few times (for ncu captures):  python tools/run_one.py KIND N [REPS]
-KIND in {strict, tf32, bf16, bf16_obf16, s8, s8_requant, bf16x3, bf16x2, f16x2}."""
+KIND in {strict, tf32, bf16, bf16_obf16, s8, s8_requant, bf16x3, bf16x2, f16x2, mxf4, generic}."""
 import os
 import sys
 
@@ -16,6 +16,17 @@ if kind == "s8":
     A = torch.randint(-127, 128, (n, n), device=dev, dtype=torch.int8)
     B = torch.randint(-127, 128, (n, n), device=dev, dtype=torch.int8)
     fn = lambda: g.gemm_s8s32(A, B)
+elif kind == "mxf4":
+    A = torch.rand(n, n, device=dev) - 0.5
+    B = torch.rand(n, n, device=dev) - 0.5
+    def fn():
+        qa, sfa, _, _ = g.mxf4_quantize(A)
+        qb, sfb, _, _ = g.mxf4_quantize(B, transpose=True)
+        g.gemm_mxf4(qa, sfa, qb, sfb, n, n, n)
+elif kind == "generic":          # unaligned pitch: the CUDA-core fallback (strict mode, so no split pre-pass takes it)
+    A = (torch.rand(n, n + 1, device=dev) - 0.5)[:, :n]
+    B = (torch.rand(n, n + 3, device=dev) - 0.5)[:, :n]
+    fn = lambda: g.gemm_f32(A, B, mode=0)
 elif kind == "s8_requant":
     A = torch.randint(-127, 128, (n, n), device=dev, dtype=torch.int8)
     B = torch.randint(-127, 128, (n, n), device=dev, dtype=torch.int8)

@@ -36,8 +36,14 @@ def to_bytes(val, unit):
 
 def main():
     rnd, names = sys.argv[1], sys.argv[2:]
-    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
-    traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+    out_dir = os.environ.get("B200_SUMMARY_DIR", os.path.join(ROOT, "profiles"))     # on the GPU box: gpurun_out/summaries (only gpurun_out/ travels back)
+    os.makedirs(out_dir, exist_ok=True)
+    traffic_path = os.path.join(out_dir, "traffic.json")
+    if not os.path.exists(traffic_path) and os.path.exists(os.path.join(ROOT, "profiles", "traffic.json")):
+        traffic_path_src = os.path.join(ROOT, "profiles", "traffic.json")
+    else:
+        traffic_path_src = traffic_path
+    traffic = json.load(open(traffic_path_src)) if os.path.exists(traffic_path_src) else {}
     for name in names:
         rep = os.path.join(ROOT, "gpurun_out", name + ".ncu-rep")
         rows = ncu_csv(rep, "raw")
@@ -82,7 +88,7 @@ def main():
             lines.append("hottest SASS lines:")
             for n, s in sorted(per, key=lambda x: -x[0])[:12]:
                 lines.append(f"  {n:7d}  {s}")
-        path = os.path.join(ROOT, "profiles", f"{rnd}_{name}.txt")
+        path = os.path.join(out_dir, f"{rnd}_{name}.txt")
         open(path, "w").write("\n".join(lines) + "\n")
         print("wrote", path)
     try:
