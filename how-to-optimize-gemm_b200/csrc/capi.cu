@@ -587,7 +587,7 @@ int launch_f16_split_rows(const float* A, long long lda, int rows, int cols, flo
 // another buffer to clear on the way (the idle half of the double-buffered maxima), or null.
 int launch_f16_split_cols(const float* B, long long ldb, int rows, int cols, float* cmax, uint16_t* planes,
                           long long pitch, int plane_rows, float* zero_buf, int zero_n, cudaStream_t st) {
-  launch_pdl(col_absmax_kernel, dim3((cols + 1023) / 1024, (rows + 31) / 32), dim3(256), 0, st, 1, B, (long long)ldb, rows, cols,
+  launch_pdl(col_absmax_kernel, dim3((cols + 1023) / 1024, (rows + 15) / 16), dim3(256), 0, st, 1, B, (long long)ldb, rows, cols,
              reinterpret_cast<unsigned int*>(cmax));
   const int gx = (int)((pitch + 2047) / 2048);
   int gy = (t_ctx->sms * 8 + gx - 1) / gx;

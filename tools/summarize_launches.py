@@ -25,7 +25,7 @@ tot = sum(per_step.values())
 lines = [f"# {os.path.basename(src)}: {len(rows)} launches; per-kernel mean device time (us)"]
 for k, v in agg.items():
     lines.append(f"{len(v):5d} x {sum(v) / len(v):10.2f} us  (min {min(v):.2f}, max {max(v):.2f})  {k[:100]}")
-lines.append("\n# one bench step (device path, N=1) = 1 x split_planes (A and B in one launch) + 1 x gemm_tc;")
+lines.append("\n# one bench step (device path, N=1, default mode) = split_f16_rows (A) + col_absmax (B) + split_f16_cols (B) + gemm_tc;")
 lines.append("# full-size launches only (the e2e leg runs the same kernels on 1024-row blocks); shares of the step:")
 for k, v in per_step.items():
     lines.append(f"  {v:10.2f} us  {100 * v / tot:5.1f} %  {len(full[k])} launches  {k[:100]}")

@@ -77,10 +77,16 @@ def main():
             for r in src[2:]:
                 if len(r) < len(h):
                     continue
-                n = int(r[ix["# Samples"]] or 0)
+                try:
+                    n = int(r[ix["# Samples"]] or 0)
+                except ValueError:          # a multi-kernel report repeats its header rows
+                    continue
                 samples += n
                 for s in stalls:
-                    tot[s] += int(r[ix[s]] or 0)
+                    try:
+                        tot[s] += int(r[ix[s]] or 0)
+                    except ValueError:
+                        pass
                 per.append((n, r[ix["Source"]].strip()[:80]))
             lines.append(f"\nwarp stall sampling, {samples} samples:")
             for s, v in sorted(tot.items(), key=lambda x: -x[1])[:8]:
