@@ -104,6 +104,8 @@ struct DevCtx {
   float* cmax_buf = nullptr;
   size_t cmax_cap = 0;
   int cmax_dirty[2] = {0, 0};       // entries of each half that may be non-zero
+  cudaStream_t aux = nullptr;        // B's pre-pass chain runs here, beside A's on the caller's stream
+  cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
   // host-pointer entry points
   std::mutex host_mu;
   Scratch scr[4];
@@ -239,6 +241,7 @@ int last_launch_status() {
 // Launch with the programmatic-serialisation (PDL) attribute: the kernel may start while the previous kernel of
 // the stream drains; every kernel launched through here calls griddep_wait before it touches global memory.
 int g_pdl = 1;                // tuning hook (b200_gemm_debug_set_pdl)
+int g_prepass_fork = 1;       // F16X2: B's pre-pass chain on an auxiliary stream beside A's (b200_gemm_debug_set_pdl bit 1 = off)
 int g_dynamic_sched = 0;      // 1: every tensor-core launch draws its tiles from an atomic counter (b200_gemm_debug_set_dynamic_sched).  Default: static
                               // round robin (measured 0-8 % faster when the GPU is ours alone) except where t_dynamic_sched asks for it
 template <typename... KArgs, typename... Args>
@@ -664,12 +667,21 @@ int gemm_f32_split_f16(int m, int n, int k, const float* A, int lda, const float
   ws_acquire(st);
   struct Release { cudaStream_t s; ~Release() { ws_release(s); } } rel{st};
   uint8_t* base = reinterpret_cast<uint8_t*>(t_ctx->ws.p);
-  if (prepA) oa = *prepA;
-  else {
-    uint16_t* pA = reinterpret_cast<uint16_t*>(base);
-    float* rmax = reinterpret_cast<float*>(base + r_off);
-    if (int rc = launch_f16_split_rows(A, lda, m, k, rmax, pA, pka, m, st)) return rc;
-    oa = F16Operand{pA, pka, m, rmax};
+  // Neither pre-pass kernel saturates HBM on its own (ncu: 37-52 % of peak DRAM throughput each), and A's and B's
+  // chains are independent: when both operands are split here, B's chain (column maxima, split) runs on the
+  // context's auxiliary stream beside A's row split and joins before the GEMM.
+  DevCtx* c = t_ctx;
+  const bool fork = !prepA && !prepB && g_prepass_fork && (double)m * k + (double)k * n >= 4.0e6;
+  cudaStream_t sb = st;
+  if (fork) {
+    if (!c->aux) {
+      if (cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&c->aux_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&c->aux_join, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return B200_ERR_NO_DEVICE; }
+    }
+    cudaEventRecord(c->aux_fork, st);
+    cudaStreamWaitEvent(c->aux, c->aux_fork, 0);
+    sb = c->aux;
   }
   if (prepB) ob = *prepB;
   else {
@@ -677,8 +689,19 @@ int gemm_f32_split_f16(int m, int n, int k, const float* A, int lda, const float
     float *cmax, *other;
     int other_dirty;
     if (int rc = cmax_reserve(n, &cmax, &other, &other_dirty)) return rc;
-    if (int rc = launch_f16_split_cols(B, ldb, k, n, cmax, pB, pnb, kp, other, other_dirty, st)) return rc;
+    if (int rc = launch_f16_split_cols(B, ldb, k, n, cmax, pB, pnb, kp, other, other_dirty, sb)) return rc;
     ob = F16Operand{pB, pnb, kp, cmax};
+  }
+  if (prepA) oa = *prepA;
+  else {
+    uint16_t* pA = reinterpret_cast<uint16_t*>(base);
+    float* rmax = reinterpret_cast<float*>(base + r_off);
+    if (int rc = launch_f16_split_rows(A, lda, m, k, rmax, pA, pka, m, st)) return rc;
+    oa = F16Operand{pA, pka, m, rmax};
+  }
+  if (fork) {
+    cudaEventRecord(c->aux_join, c->aux);
+    cudaStreamWaitEvent(st, c->aux_join, 0);
   }
   return gemm_f16x2_core(m, n, k, oa, ob, C, ldc, acc, st);
 }
@@ -831,7 +854,7 @@ void b200_gemm_set_default_f32_mode(int mode) {
 }
 void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes) { g_dbg_b_lbo = lbo_bytes; g_dbg_b_sbo = sbo_bytes; }
 void b200_gemm_debug_set_bn(int bn) { g_force_bn = bn; }
-void b200_gemm_debug_set_pdl(int on) { g_pdl = on != 0; }
+void b200_gemm_debug_set_pdl(int v) { g_pdl = (v & 1) != 0; g_prepass_fork = (v & 2) == 0; }
 void b200_gemm_debug_set_dynamic_sched(int on) { g_dynamic_sched = on != 0; }
 void b200_gemm_debug_set_cta_group(int cg) { g_force_cg = cg; }
 void b200_gemm_debug_set_split_tail(int on) { g_split_tail = on; }

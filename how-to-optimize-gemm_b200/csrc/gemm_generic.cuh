@@ -122,14 +122,6 @@ __global__ void scale_inplace_kernel(int M, int N, float* __restrict__ C, long l
 }
 
 template <typename T>
-__global__ void add_inplace_kernel(int M, int N, T* __restrict__ C, long long ldc,
-                                   const T* __restrict__ Tm, long long ldt) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= N) return;
-  for (int i = blockIdx.y; i < M; i += gridDim.y) C[(long long)i * ldc + j] += Tm[(long long)i * ldt + j];
-}
-
-template <typename T>
 __global__ void fill_zero_kernel(int M, int N, T* __restrict__ C, long long ldc) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= N) return;

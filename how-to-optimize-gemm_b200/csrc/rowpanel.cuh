@@ -180,7 +180,7 @@ int b200_rowpanel_create(b200_rowpanel** out, void* nccl_comm, int m_local_max, 
   rp->m_max = m_local_max; rp->n = n; rp->k = k;
   rp->mode = resolve_f32_mode(precision_mode);
   // K-slices: the caller's row counts (must add up to k, boundaries multiples of 8), else by default
-  // one slice on a single rank and two slices weighted 1 : 3 otherwise.
+  // one slice on a single rank, two slices weighted 1 : 3 up to 256 MB of B, equal ~256 MB slices beyond.
   if (n_slices > 0 && slice_rows) {
     int acc = 0;
     for (int j = 0; j < n_slices; j++) {
@@ -192,13 +192,20 @@ int b200_rowpanel_create(b200_rowpanel** out, void* nccl_comm, int m_local_max, 
   } else if (rp->world == 1 || k < 1024) {
     rp->nslices = 1; rp->k0[0] = 0; rp->k0[1] = k;
   } else {
-    // two slices, 1 : 3.  Every extra slice costs a GEMM launch with its own pass over C (~30 us at 4096^2) and every
-    // ncclBroadcast ~40 us of fixed latency, so more slices lose more than a shorter first slice gains (measured on
-    // 2 x B200, profiles/r02_rowpanel_trace.txt: [512,1536,2048] 0.58 ms, [2048,2048] 0.48, [1024,3072] 0.47).
-    rp->nslices = 2;
+    // Up to 256 MB of B: two slices, 1 : 3.  Every extra slice costs a GEMM launch with its own pass over C (~30 us at
+    // 4096^2) and every ncclBroadcast ~40 us of fixed latency, so at 64 MB more slices lose more than a shorter first
+    // slice gains (measured on 2 x B200, profiles/r02_rowpanel_trace.txt: [512,1536,2048] 0.58 ms, [2048,2048] 0.48,
+    // [1024,3072] 0.47).  Larger operands (BASELINE config 5: 1 GiB) amortise those costs: equal slices of ~256 MB, so
+    // that only a quarter of the exchange, not the first 256 MB + everything the math could not cover, stays exposed
+    // (8 GPUs, 16384^3, two slices: 3.96 ms against ~2.3 ms of math per rank).
+    const double bytes = (double)k * n * 4.0;
+    int ns = (int)((bytes + 268435455.0) / 268435456.0);
+    ns = ns < 2 ? 2 : (ns > 8 ? 8 : ns);
+    rp->nslices = ns;
     rp->k0[0] = 0;
-    rp->k0[1] = (int)(((long long)k / 4 + 63) / 64 * 64);
-    rp->k0[2] = k;
+    if (ns == 2) rp->k0[1] = (int)(((long long)k / 4 + 63) / 64 * 64);
+    else for (int j = 1; j < ns; j++) rp->k0[j] = (int)(((long long)k * j / ns + 63) / 64 * 64);
+    rp->k0[ns] = k;
   }
 #define RP_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cudaGetLastError(); rowpanel_free(rp); return (int)e_; } } while (0)
   RP_TRY(cudaStreamCreateWithFlags(&rp->comm_stream, cudaStreamNonBlocking));

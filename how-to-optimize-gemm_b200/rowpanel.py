@@ -24,14 +24,20 @@ def row_panel(rank, world, M):
     return r0, r0 + base + (1 if rank < extra else 0)
 
 
-def default_slices(K, world):
-    """The C++ plan's default K-slices (b200_rowpanel_create): one slice on a single rank or for a short K, else two
-    slices weighted 1 : 3 with the boundary rounded up to 64 rows — a shorter first slice shortens the only part of the
-    exchange the math cannot hide behind; more slices cost more (a GEMM launch and an NCCL call each) than they gain."""
+def default_slices(K, world, N=None):
+    """The C++ plan's default K-slices (b200_rowpanel_create): one slice on a single rank or for a short K; up to 256 MB
+    of B two slices weighted 1 : 3 (a shorter first slice shortens the only part of the exchange the math cannot hide
+    behind; more slices cost a GEMM launch and an NCCL call each); beyond that equal slices of ~256 MB (at most 8).
+    Boundaries are rounded up to 64 rows.  N defaults to K (square B)."""
     if world == 1 or K < 1024:
         return [(0, K)]
-    e1 = (K // 4 + 63) // 64 * 64
-    return [(0, e1), (e1, K)]
+    N = K if N is None else N
+    ns = max(2, min(8, -(-(K * N * 4) // (256 << 20))))
+    if ns == 2:
+        edges = [0, (K // 4 + 63) // 64 * 64, K]
+    else:
+        edges = [0] + [(K * j // ns + 63) // 64 * 64 for j in range(1, ns)] + [K]
+    return list(zip(edges[:-1], edges[1:]))
 
 
 def row_chunks(K, chunks, align=64):
@@ -121,7 +127,7 @@ class RowPanelGemm:
     def __init__(self, gemm, dist, rank, world, K, N, chunks=None, src=0, pipeline=True):
         self.gemm, self.dist = gemm, dist
         self.rank, self.world, self.src = rank, world, src
-        self.chunks = default_slices(K, world) if chunks is None else row_chunks(K, chunks)
+        self.chunks = default_slices(K, world, N) if chunks is None else row_chunks(K, chunks)
         self.pipeline = pipeline
 
     def run(self, A_local, B, C_local):

@@ -211,7 +211,7 @@ int b200_gemm_s8s8_requant(int m, int n, int k,
  *               made with b200_comm_unique_id + b200_comm_init_rank (rank 0 creates the 128-byte id and
  *               hands it to the other ranks by whatever means the host has).  NULL = single rank.
  *   slice_rows  rows of B per K-slice (sum k, every boundary a multiple of 8), or NULL / n_slices 0 for the
- *               default (one slice on one rank, else two slices weighted 1:3).
+ *               default (one slice on one rank; two slices weighted 1:3 up to 256 MB of B; equal ~256 MB slices, at most 8, beyond).
  * The plan owns all scratch (planes, events, streams): the compute calls never allocate. */
 typedef struct b200_rowpanel b200_rowpanel;
 int  b200_nccl_load(const char* libnccl_path_or_null);
@@ -275,7 +275,7 @@ void b200_gemm_debug_set_b_desc(int lbo_bytes, int sbo_bytes);
 /* Tuning hook: 0 = launch without programmatic dependent launch (default 1: the library's tensor-core and
  * pre-pass kernels are launched with the programmatic-serialisation attribute and order themselves with
  * griddepcontrol.wait, so a kernel's prologue overlaps the tail of its predecessor in the stream). */
-void b200_gemm_debug_set_pdl(int on);
+void b200_gemm_debug_set_pdl(int mask);   /* bit 0: PDL on; bit 1: keep the F16X2 pre-pass of B on the caller's stream (default: auxiliary stream beside A's) */
 /* Tuning hook: 0 = static round-robin tile schedule (default 1: a scheduler warp hands tiles out from an atomic
  * counter, so CTAs that start late because a co-running kernel holds their SM draw fewer tiles). */
 void b200_gemm_debug_set_dynamic_sched(int on);

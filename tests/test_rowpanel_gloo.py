@@ -87,7 +87,9 @@ def test_partition_helpers():
     # the C++ plan's default schedule (b200_rowpanel_create), mirrored by default_slices
     assert rowpanel.default_slices(4096, 1) == [(0, 4096)]
     assert rowpanel.default_slices(4096, 2) == [(0, 1024), (1024, 4096)]
-    assert rowpanel.default_slices(16384, 8) == [(0, 4096), (4096, 16384)]
+    assert rowpanel.default_slices(16384, 8) == [(0, 4096), (4096, 8192), (8192, 12288), (12288, 16384)]     # 1 GiB: 4 x 256 MB
+    assert rowpanel.default_slices(8192, 2) == [(0, 2048), (2048, 8192)]                                     # 256 MB: still two slices
+    assert len(rowpanel.default_slices(65536, 4, 16384)) == 8
     assert rowpanel.default_slices(1000, 4) == [(0, 1000)]
     assert rowpanel.default_slices(1100, 2) == [(0, 320), (320, 1100)]
     for K in (1, 63, 64, 200, 4096, 16384):

@@ -104,6 +104,7 @@ def _worker(rank, world, port, M, N, K, out_dir):
             B = torch.from_numpy(b).to(dev) if rank == 0 else torch.full((K, N), float("nan"), device=dev)
             C = torch.full((r1 - r0, N), float("nan"), device=dev)
             plan = rp.RowPanelPlan(g, comm, r1 - r0, N, K, mode, slices)
+            assert plan.chunks == (slices or rp.default_slices(K, world, N)), plan.chunks      # the C++ default == its Python model
             for _ in range(3):                       # back-to-back steps reuse the plan's buffers and events
                 plan.run(A, B, C)
             torch.cuda.synchronize()
