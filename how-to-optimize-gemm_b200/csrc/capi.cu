@@ -298,6 +298,8 @@ int g_group_rows = 0;         // tuning hook: rows per raster group of the tenso
 int g_force_cg = 0;           // test/tuning hook (b200_gemm_debug_set_cta_group): 0 = auto, 1, 2
 int g_epi8 = 1;               // pair kernels of the plain kinds drain with 8 epilogue warps (tuning hook b200_gemm_debug_set_epilogue bit 1 = back to 4):
                               // measured int8 4096^3 2.07 -> 2.32 POP/s, bf16->fp32 2304^3 692 -> 823 TFLOP/s, bit-identical results
+constexpr int kStreamCDefault = 0;
+int g_stream_c = -1;          // split modes: streaming stores for C (-1 = unresolved: B200GEMM_STREAM_C or the default above)
 int g_epi_direct = 0;         // tuning hook (b200_gemm_debug_set_epilogue): 1 = direct register stores for non-folding passes
 int g_ffma_fat = -1;          // strict kernel: 1 = 128x256 fat-thread variant, 0 = 128x128, -1 = by size
 int g_ffma_halves = 1;        // strict kernel: split the tail round into half tiles (tuning hook)
@@ -336,6 +338,7 @@ int launch_tc(int m, int n, int k, const void* A, long long lda, int a_rows_tota
   p.accumulate = accumulate;
   p.axpby = t_epi.axpby; p.alpha = t_epi.alpha; p.beta = t_epi.beta;
   p.epi_direct = g_epi_direct;
+  p.stream_c = g_stream_c < 0 ? (g_stream_c = (getenv("B200GEMM_STREAM_C") ? atoi(getenv("B200GEMM_STREAM_C")) : kStreamCDefault)) : g_stream_c;
   auto kern = gemm_tc_kernel<KIND, BN, STAGES, OutT, Prod, A_ROW_BYTES, CG, EPIW>;
   if (int arc = ensure_smem_attr(kern, Cfg::SMEM_BYTES)) return arc;
   int tiles = p.tiles_m * p.tiles_n;

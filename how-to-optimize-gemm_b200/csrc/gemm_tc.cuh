@@ -91,6 +91,7 @@ struct TcParams {
   float alpha, beta;
   int axpby;
   int accumulate;
+  int stream_c;       // 1: the split modes' single pass over C uses streaming (evict-first) stores, so C does not push the operand planes out of L2
   int epi_direct;     // 1: non-folding passes store straight from registers (tuning hook)          // 1: C += A*B (every partial, including the first, is folded into C); fp32/int32 only
   int dbg_b_lbo, dbg_b_sbo;  // 0 = defaults (probe hook, see b200_gemm_debug_set_b_desc)
 };
@@ -599,7 +600,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   if (p.axpby) { v.x = fmaf(be, o.x, v.x); v.y = fmaf(be, o.y, v.y); v.z = fmaf(be, o.z, v.z); v.w = fmaf(be, o.w, v.w); }
                   else { v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
                 }
-                *reinterpret_cast<float4*>(dst) = v;
+                if (p.stream_c) __stcs(reinterpret_cast<float4*>(dst), v);
+                else *reinterpret_cast<float4*>(dst) = v;
               } else {
                 const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll

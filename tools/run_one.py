@@ -9,6 +9,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import _libs
 
 g = _libs.load_pkg()
+if os.environ.get("B200_GROUP_ROWS"):            # tuning: rows of A per raster group of the tensor-core kernels
+    g.lib.b200_gemm_debug_set_group_rows(int(os.environ["B200_GROUP_ROWS"]))
 kind, n = sys.argv[1], int(sys.argv[2])
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 dev = "cuda"
