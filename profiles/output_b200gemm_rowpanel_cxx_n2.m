@@ -1,0 +1,6 @@
+NCCL version 2.27.3+cuda12.9
+version = 'b200gemm_rowpanel_cxx';
+% b200gemm 0.2 (sm_100a; tcgen05+TMA; round 2); M = 2 x 4096 rows, N = 4096, K = 4096, B broadcast from rank 0 inside every call
+MY_MMult = [
+2 677752.32 3.822558e-06 
+];

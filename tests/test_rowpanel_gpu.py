@@ -143,3 +143,28 @@ def test_rowpanel_two_nccl_ranks_full_c(tmp_path, oracle):
             assert np.array_equal(H, naive)
         else:
             assert rel(H, t) <= TOL[mode]
+
+
+def _demo(*args):
+    import subprocess
+    exe = os.path.join(_libs.ROOT, _libs.PKG, "harness", "rowpanel_demo.x")
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built (make -C {_libs.PKG} host)")
+    r = subprocess.run([exe, *[str(a) for a in args]], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    row = r.stdout.split("MY_MMult = [")[1].split("];")[0].split()
+    return int(row[0]), float(row[1]), float(row[2])
+
+
+def test_cxx_host_single_gpu():
+    """harness/rowpanel_demo.cpp: a C++ program (no Python, no torch) driving the plan through include/b200gemm.h."""
+    gpus, gflops, err = _demo(1, 1024, 1280, 1536, 5)
+    assert gpus == 1 and gflops > 0 and err <= 1e-5
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_cxx_host_two_gpus_one_thread_each():
+    """One process, one host thread per GPU (per-device library state), NCCL communicator made through the C ABI
+    (b200_comm_unique_id / b200_comm_init_rank), libnccl resolved by dlopen."""
+    gpus, gflops, err = _demo(2, 1024, 1280, 1536, 5)
+    assert gpus == 2 and gflops > 0 and err <= 1e-5
