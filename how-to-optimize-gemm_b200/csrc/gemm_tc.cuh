@@ -1076,10 +1076,13 @@ __global__ void __launch_bounds__(256) col_absmax_kernel(const float* __restrict
       if (c + 3 < cols) mx.w = fmaxf(mx.w, fabsf(s[3]));
     }
   }
-  atomicMax(out + c, __float_as_uint(mx.x));
-  if (c + 1 < cols) atomicMax(out + c + 1, __float_as_uint(mx.y));
-  if (c + 2 < cols) atomicMax(out + c + 2, __float_as_uint(mx.z));
-  if (c + 3 < cols) atomicMax(out + c + 3, __float_as_uint(mx.w));
+  // Only a block that can raise the running maximum touches it: hundreds of row blocks hit the same 4 addresses and
+  // same-address atomics serialise in L2 (ncu: this kernel sat at 37 % of peak DRAM throughput); after the first few
+  // blocks almost every candidate is below the current value.  A stale (smaller) value read here only costs an atomic.
+  const float m4[4] = {mx.x, mx.y, mx.z, mx.w};
+#pragma unroll
+  for (int e = 0; e < 4; e++)
+    if (c + e < cols && __float_as_uint(m4[e]) > __ldcg(out + c + e)) atomicMax(out + c + e, __float_as_uint(m4[e]));
 }
 
 // B side: a thread owns 8 consecutive columns (their scale exponents live in registers) and walks rows
