@@ -58,14 +58,16 @@ enum b200_f32_mode {
   B200_F32_TF32   = 1,   /* one tcgen05 kind::tf32 pass (10-bit mantissa inputs,
                             fp32 accumulate in TMEM)                              */
   B200_F32_BF16X3 = 2,   /* split-bf16: a=a1+a2+a3, 6 tcgen05 kind::f16 products per
-                            k-step, two-level accumulation (K chunks of 512 folded
-                            into C with rounded fp32 adds): fp32-class error on the
+                            k-step, two-level accumulation (K chunks of 512, each a
+                            fresh TMEM accumulator added with a rounded fp32 add to a
+                            running sum held in registers): fp32-class error on the
                             tensor cores, elementwise.  The round-1 default.      */
   B200_F32_BF16X2 = 3,   /* split-bf16: a=a1+a2, 3 products, ~2^-17 relative       */
   B200_F32_AUTO   = 4,   /* library default: F16X2 unless the environment variable
                             B200GEMM_F32_MODE or b200_gemm_set_default_f32_mode
                             says otherwise; problems up to ~512^3 with TMA-able
-                            operands take the single-launch STRICT kernel          */
+                            operands take the single-launch STRICT kernel, problems
+                            up to ~1100^3 the two-launch BF16X3 path               */
   B200_F32_F16X2  = 5    /* scaled split-fp16: rows of A / columns of B are scaled by
                             exact powers of two into [-1,1], a'=h1+h2 in fp16 (22
                             bits), 3 tcgen05 kind::f16 products, two-level
